@@ -1,0 +1,143 @@
+/*
+ * sawfish_cuda.h — C ABI of libsawfish_cuda.so, the B200 (sm_100a) drop-in for the
+ * pairwise-alignment hot path of PacificBiosciences/sawfish.
+ *
+ * What it replaces in the reference (paths relative to the sawfish repository):
+ *   - rust_wfa2::aligner::{WFAligner, WFAlignerGapLinear, WFAlignerGapAffine2Pieces}
+ *     as used by src/wfa2_utils.rs:5-8,116,130,135,159-169,183-190,216-218
+ *     (the FFI into WFA2-lib that `wfa2_utils::PairwiseAligner` wraps);
+ *   - process_wfa2_cigar_string                       src/wfa2_utils.rs:13-95
+ *   - PairwiseAligner::{new_large_indel_aligner,new_consensus_aligner,set_text,align,
+ *     align_clip_frac,align_end_to_end}               src/wfa2_utils.rs:143-251
+ *   - the per-pair call loops that become batches:    src/score_sv/mod.rs:837-901,
+ *     src/refine_sv/align/mod.rs:387-451,1991-2049
+ *
+ * Conventions: plain pointers and sizes only; every entry point returns 0 or a negative
+ * sfc_error and never unwinds; the caller owns all host buffers, the library owns device
+ * memory; one sfc_ctx per (host thread, GPU), no global state.  There is NO CPU fallback:
+ * without a CUDA device sfc_create fails with SFC_ERR_NO_DEVICE.
+ *
+ * The reference-side binding (a `sawfish-cuda` crate: build.rs + extern "C" block) is in
+ * INTEGRATION.md.
+ */
+#ifndef SAWFISH_CUDA_H
+#define SAWFISH_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFC_ABI_VERSION 1
+
+typedef struct sfc_ctx sfc_ctx; /* opaque: device buffers + stream for ONE GPU */
+
+typedef enum {
+  SFC_OK = 0,
+  SFC_ERR_INVALID = -1,     /* bad argument (NULL, empty sequence, clip > length, match > 0 ...) */
+  SFC_ERR_NO_DEVICE = -2,   /* no CUDA device / wrong architecture */
+  SFC_ERR_CUDA = -3,        /* CUDA runtime error; see sfc_last_error */
+  SFC_ERR_CAPACITY = -4,    /* caller's output buffer too small */
+  SFC_ERR_UNSUPPORTED = -5, /* symbol outside {A,C,G,T,N,a,c,g,t,n}, or sequence too long for shared memory */
+  SFC_ERR_OOM = -6          /* device workspace exhausted even with one pair in flight */
+} sfc_error;
+
+/* Per-pair status, mirrors rust_wfa2::aligner::AlignmentStatus so the caller can keep its
+ * assert_eq!(status, StatusAlgCompleted) (src/wfa2_utils.rs:117). */
+enum { SFC_STATUS_COMPLETED = 0, SFC_STATUS_UNSUPPORTED = -5, SFC_STATUS_OOM = -6, SFC_STATUS_MAX_SCORE = -7 };
+
+/* metric 0 = gap-linear (indel penalty = gap_ext1; gap_open1 ignored)   WFAlignerGapLinear::new_with_match
+ * metric 1 = gap-affine 2-piece                                          WFAlignerGapAffine2Pieces::new_with_match
+ * match <= 0, others are penalties (positive), exactly the integers sawfish passes
+ * (src/wfa2_utils.rs:159-168: -1,3,1,2,60,0 and :183-189: -1,3,2). */
+typedef struct {
+  int32_t metric;
+  int32_t match, mismatch, gap_open1, gap_ext1, gap_open2, gap_ext2;
+} sfc_penalties;
+
+/* One (pattern, text) pair.  Offsets are byte offsets into seq_arena (forward ASCII).
+ * The four ends-free allowances are what rust-wfa2's align_ends_free takes
+ * (src/wfa2_utils.rs:116,130); all zero == align_end_to_end (src/wfa2_utils.rs:135).
+ * flags bit0: reverse both sequences before aligning (sawfish convention, wfa2_utils.rs:198-215). */
+typedef struct {
+  uint64_t pattern_off, text_off;
+  uint32_t pattern_len, text_len;
+  int32_t pattern_begin_free, pattern_end_free, text_begin_free, text_end_free;
+  uint32_t flags;
+} sfc_pair;
+#define SFC_PAIR_REVERSE 1u
+
+/* Run-length WFA ops: (run_length << 2) | code, in WFA2's cigar order (begin -> end of the
+ * sequences as aligned, i.e. of the REVERSED sequences when SFC_PAIR_REVERSE is set).
+ * 'I' consumes text, 'D' consumes pattern, as in WFA2-lib. */
+enum { SFC_OP_M = 0, SFC_OP_X = 1, SFC_OP_I = 2, SFC_OP_D = 3 };
+
+typedef struct {
+  double h2d_ms, pack_ms, kernel_ms, d2h_ms; /* CUDA-event times of the last batch on the ctx stream */
+  uint64_t h2d_bytes, d2h_bytes;
+  uint64_t cells;            /* M-wavefront cells computed by the kernels (device counters) */
+  uint32_t launches;         /* kernels launched for the last batch */
+  uint32_t retries;          /* workspace-escalation passes */
+  uint32_t n_score_kernel;   /* pairs served by the score-only kernel (K1) */
+  uint32_t n_align_kernel;   /* pairs served by the backtrace kernel (K2) */
+} sfc_batch_stats;
+
+/* ---- context ---- */
+int sfc_abi_version(void);
+int sfc_device_count(void);
+int sfc_create(int device_ordinal, sfc_ctx** out);
+void sfc_destroy(sfc_ctx*);
+const char* sfc_last_error(const sfc_ctx*);
+/* Upper bound on device workspace the ctx may allocate (bytes); 0 = 80% of free memory. */
+int sfc_set_workspace_limit(sfc_ctx*, size_t bytes);
+
+/* ---- the batched hot path ---- */
+/* One-shot: upload + pack + align + download.  scores/status: [n_pairs].
+ * want_cigar == 0: ops_* may be NULL.  Otherwise ops_off is [n_pairs+1] and pair i's runs are
+ * ops_rle[ops_off[i] .. ops_off[i+1]); SFC_ERR_CAPACITY if ops_cap (in uint32 entries) is too small
+ * (ops_off[n_pairs] then holds the required size). */
+int sfc_align_batch(sfc_ctx*, const sfc_penalties*, const uint8_t* seq_arena, size_t arena_len,
+                    const sfc_pair* pairs, size_t n_pairs, int want_cigar,
+                    int32_t* scores, int32_t* status,
+                    uint32_t* ops_rle, size_t ops_cap, uint64_t* ops_off);
+
+/* Staged form of the same call (what a pipelined submitter thread uses; also how bench.py separates
+ * device-resident throughput from end-to-end throughput). */
+int sfc_batch_upload(sfc_ctx*, const uint8_t* seq_arena, size_t arena_len, const sfc_pair* pairs, size_t n_pairs);
+int sfc_batch_run(sfc_ctx*, const sfc_penalties*, int want_cigar);
+int sfc_batch_download(sfc_ctx*, int32_t* scores, int32_t* status,
+                       uint32_t* ops_rle, size_t ops_cap, uint64_t* ops_off);
+int sfc_batch_get_stats(const sfc_ctx*, sfc_batch_stats* out);
+
+/* ---- CIGAR helpers (host, exact restatements of the reference's host code) ---- */
+/* Expand run-length ops to WFA2's byte string ('M','X','I','D'). Returns bytes written or <0. */
+int64_t sfc_expand_ops(const uint32_t* ops_rle, size_t n_runs, uint8_t* wfa_ops, size_t cap);
+/* == process_wfa2_cigar_string (src/wfa2_utils.rs:13-95): htslib-encoded cigar (len<<4|op). */
+int sfc_translate_cigar(const uint8_t* wfa_ops, size_t n_ops, int64_t* ref_offset,
+                        uint32_t* cigar, size_t cigar_cap, size_t* n_cigar, int* has_match);
+/* Same, straight from run-length ops (no expansion). */
+int sfc_translate_rle(const uint32_t* ops_rle, size_t n_runs, int64_t* ref_offset,
+                      uint32_t* cigar, size_t cigar_cap, size_t* n_cigar, int* has_match);
+
+/* ---- per-pair convenience mirroring wfa2_utils::PairwiseAligner (n = 1 batches) ---- */
+typedef struct sfc_aligner sfc_aligner;
+int sfc_aligner_new_consensus(sfc_ctx*, sfc_aligner** out);                       /* wfa2_utils.rs:182-196 */
+int sfc_aligner_new_large_indel(sfc_ctx*, int is_long_contig, sfc_aligner** out); /* wfa2_utils.rs:149-175 */
+void sfc_aligner_free(sfc_aligner*);
+int sfc_aligner_set_text(sfc_aligner*, const uint8_t* text, size_t len);          /* wfa2_utils.rs:198-203 */
+/* mode 0 = align (clip 0.4 rule, wfa2_utils.rs:106-118), 1 = align_clip_frac (:120-132), 2 = align_end_to_end (:134-140).
+ * Outputs the post-translation result: score, has_alignment, ref_offset, cigar. */
+int sfc_aligner_align(sfc_aligner*, const uint8_t* pattern, size_t len, int mode,
+                      double text_clip_frac, double pattern_clip_frac,
+                      int32_t* score, int* has_alignment, int64_t* ref_offset,
+                      uint32_t* cigar, size_t cigar_cap, size_t* n_cigar);
+
+/* ---- measurement helper: integer-ALU roofline denominator (IADD3/LOP3 issue rate) ---- */
+/* Runs a dependent-chain-free INT32 micro-benchmark and returns giga-ops/s (thread-level ops). */
+int sfc_measure_int_peak(sfc_ctx*, double* gops_per_s, double* sm_clock_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,489 @@
+// sfc_k_align.cuh — K2: ends-free wavefront alignment WITH backtrace (gap-affine 2-piece or gap-linear).
+//
+// Replaces WFA2-lib's WFAlignerGapAffine2Pieces / WFAlignerGapLinear in AlignmentScope::Alignment as
+// sawfish's refine_sv drives them: PairwiseAligner::new_large_indel_aligner + set_text + align
+// (reference src/wfa2_utils.rs:149-175,198-219), called per contig at
+// src/refine_sv/align/mod.rs:439-451 and :2027-2049 where the full CIGAR is consumed.
+//
+// Mapping: one CTA per pair (persistent CTAs pull pairs from a global work counter).
+//   * sequences: 4-bit, overlapped 8-byte windows in shared memory (one LDS.64 + one funnel shift per
+//     8-base compare; warp-cooperative 256-base rounds for long match runs);
+//   * wavefront rings (M depth max(x',o1'+e1',o2'+e2')+1, I1/D1 depth e1'+1, I2/D2 depth e2'+1) live in
+//     the CTA's slab of device memory (HBM/L2) — a 20 kb x 20 kb pair needs ~22 MB of ring;
+//   * reads of source wavefronts are range-guarded from per-wavefront (lo,hi) metadata kept in shared
+//     memory, so rings are never initialised or cleared; trimming of every component to its first/last
+//     in-matrix diagonal is metadata only (one 11-way block reduction per score);
+//   * backtrace: instead of keeping every wavefront (WFA2 MemoryHigh) the kernel records ONE choice byte per
+//     (score, diagonal) at compute time using WFA2's tie-break priority
+//     (X > D2 > D1 > I2 > I1, extend >= open), walks the bytes back to score 0 (also yields k0 for the
+//     score formula), then replays forward with greedy match extension to emit run-length ops.
+//     This is the same path WFA2's offset-comparing backtrace takes (validated against the oracle's
+//     LITERAL mode).
+// Bound by integer ALU issue + L2/HBM traffic of the rings (~50 B per diagonal per score); no tensor cores.
+#pragma once
+#include "sfc_device.cuh"
+
+namespace sfc {
+
+enum { K2_SEL_X = 0, K2_SEL_I1 = 1, K2_SEL_I2 = 2, K2_SEL_D1 = 3, K2_SEL_D2 = 4 };
+constexpr uint32_t K2_BIT_I1E = 0x08, K2_BIT_I2E = 0x10, K2_BIT_D1E = 0x20, K2_BIT_D2E = 0x40;
+enum { K2_E_X = 0, K2_E_IO = 1, K2_E_IE = 2, K2_E_DO = 3, K2_E_DE = 4 };  // backward edit codes
+enum { K2_C_M = 0, K2_C_I1 = 1, K2_C_D1 = 2, K2_C_I2 = 3, K2_C_D2 = 4 };
+
+struct K2Params {
+  const DevPair* pairs;
+  const uint32_t* order;
+  uint32_t n;
+  uint32_t* counter;
+  const uint32_t* nib;
+  int32_t* scores;
+  int32_t* status;
+  int metric, x, o1, e1, o2, e2, match;  // adjusted penalties (linear: e1 = indel), original match
+  int nM, nG1, nG2;                      // ring depths
+  unsigned char* slabs;
+  unsigned long long slab_bytes;
+  int want_cigar;
+  uint32_t* pool;  // run-length ops pool
+  unsigned long long pool_cap;
+  unsigned long long* pool_used;
+  unsigned long long* out_off;  // [n] offset of pair's runs in pool
+  uint32_t* out_len;            // [n]
+  unsigned long long* cells;
+  int win_cap;  // uint2 windows available in shared memory for both sequences together
+  int max_score;
+};
+
+struct K2Range {
+  int lo, hi;
+  __device__ __forceinline__ bool any() const { return lo <= hi; }
+  __device__ __forceinline__ int cnt() const { return max(hi - lo + 1, 0); }
+};
+
+__device__ __forceinline__ int32_t k2_guard(const int32_t* __restrict__ row, int k, int lo, int cnt) {
+  return ((unsigned)(k - lo) < (unsigned)cnt) ? row[k] : WNULL;
+}
+__device__ __forceinline__ bool k2_in_matrix(int32_t off, int k, int plen, int tlen) {
+  return (unsigned)off <= (unsigned)tlen && (unsigned)(off - k) <= (unsigned)plen;
+}
+__device__ __forceinline__ long long k2_gap_cost(const K2Params& P, int L) {
+  if (L <= 0) return 0;
+  if (P.metric == 0) return (long long)P.e1 * L;
+  const long long a = (long long)P.o1 + (long long)P.e1 * L, b = (long long)P.o2 + (long long)P.e2 * L;
+  return a < b ? a : b;
+}
+
+template <bool AFF>
+__global__ void __launch_bounds__(512) k2_align(const K2Params P) {
+  extern __shared__ __align__(16) unsigned char k2_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, NW = NT >> 5;
+  constexpr int NRED = AFF ? 11 : 3;
+  const int nslots = AFF ? P.nM + 2 * P.nG1 + 2 * P.nG2 : P.nM;
+  uint2* win = reinterpret_cast<uint2*>(k2_smem);
+  int* meta = reinterpret_cast<int*>(win + P.win_cap);  // [nslots][2]
+  int* part = meta + 2 * nslots;                        // [2][32][NRED]
+  int* misc = part + 2 * 32 * NRED;                     // [0] pair idx, [1..] backtrace broadcast
+  unsigned char* slab = P.slabs + (size_t)blockIdx.x * P.slab_bytes;
+  unsigned long long cells_acc = 0;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) misc[0] = (int)atomicAdd(P.counter, 1u);
+    __syncthreads();
+    const uint32_t wi = (uint32_t)misc[0];
+    if (wi >= P.n) break;
+    const uint32_t pi = P.order[wi];
+    const DevPair pr = P.pairs[pi];
+    const int plen = pr.plen, tlen = pr.tlen;
+    const int nwp = (plen >> 3) + 1, nwt = (tlen >> 3) + 1;
+    uint2* wp = win;
+    uint2* wt = win + nwp;
+    // ---- carve the slab ----
+    const int Wp = plen + tlen + 5, kbase = plen + 2;
+    long long scap_ll = k2_gap_cost(P, plen) + k2_gap_cost(P, tlen) + 1;
+    if (scap_ll > P.max_score) scap_ll = P.max_score;
+    const int S_cap = (int)scap_ll;
+    const size_t ring_bytes = ((size_t)nslots * Wp * 4 + 15) & ~(size_t)15;
+    const size_t rowoff_bytes = (((size_t)S_cap + 1) * 8 + 15) & ~(size_t)15;
+    const size_t rowlo_bytes = (((size_t)S_cap + 1) * 4 + 15) & ~(size_t)15;
+    const size_t E_cap = (size_t)plen + tlen + 8;
+    const size_t tmp_bytes = (E_cap * 4 + 15) & ~(size_t)15;
+    const size_t fixed = ring_bytes + rowoff_bytes + rowlo_bytes + 2 * tmp_bytes;
+    int res_status = 0, res_score = 0;
+    if (nwp + nwt > P.win_cap) res_status = -5;
+    else if (fixed + 1024 > P.slab_bytes) res_status = -6;
+    if (res_status != 0) {
+      if (tid == 0) { P.scores[pi] = 0; P.status[pi] = res_status; P.out_len[pi] = 0; P.out_off[pi] = 0; }
+      continue;
+    }
+    int32_t* rings = reinterpret_cast<int32_t*>(slab);
+    unsigned long long* rowoff = reinterpret_cast<unsigned long long*>(slab + ring_bytes);
+    int* rowlo = reinterpret_cast<int*>(slab + ring_bytes + rowoff_bytes);
+    uint32_t* tmp_b = reinterpret_cast<uint32_t*>(slab + ring_bytes + rowoff_bytes + rowlo_bytes);
+    uint32_t* tmp_f = tmp_b + (tmp_bytes >> 2);
+    unsigned char* bt = slab + fixed;
+    const unsigned long long bt_cap = P.slab_bytes - fixed;
+    unsigned long long bt_used = 0;
+    {
+      const uint32_t* gp = P.nib + pr.p_woff;
+      const uint32_t* gt = P.nib + pr.t_woff;
+      for (int i = tid; i < nwp; i += NT) wp[i] = make_uint2(gp[i], gp[i + 1]);
+      for (int i = tid; i < nwt; i += NT) wt[i] = make_uint2(gt[i], gt[i + 1]);
+    }
+    __syncthreads();
+
+    // slot bases per component
+    const int sbM = 0, sbI1 = P.nM, sbD1 = P.nM + P.nG1, sbI2 = P.nM + 2 * P.nG1, sbD2 = P.nM + 2 * P.nG1 + P.nG2;
+    K2Range last[5];  // metadata of score s-1 (register copy, so one barrier per score suffices)
+#pragma unroll
+    for (int c = 0; c < 5; ++c) { last[c].lo = 1; last[c].hi = -1; }
+    auto slot_of = [&](int c, int sc) -> int {
+      switch (c) {
+        case K2_C_M: return sbM + sc % P.nM;
+        case K2_C_I1: return sbI1 + sc % P.nG1;
+        case K2_C_D1: return sbD1 + sc % P.nG1;
+        case K2_C_I2: return sbI2 + sc % P.nG2;
+        default: return sbD2 + sc % P.nG2;
+      }
+    };
+
+    int s = 0, par = 0, end_k = 0;
+    bool done = false;
+    for (;; ++s) {
+      if (s > S_cap) { res_status = -7; break; }
+      // ---- source wavefronts ----
+      const int s_mx = s - P.x;
+      const int s_o1 = AFF ? s - P.o1 - P.e1 : s - P.e1;
+      const int s_o2 = s - P.o2 - P.e2, s_e1 = s - P.e1, s_e2 = s - P.e2;
+      auto get = [&](int c, int sc) -> K2Range {
+        K2Range r; r.lo = 1; r.hi = -1;
+        if (sc < 0 || s == 0) return r;
+        if (sc == s - 1) return last[c];
+        const int sl = slot_of(c, sc);
+        r.lo = meta[2 * sl]; r.hi = meta[2 * sl + 1];
+        return r;
+      };
+      const K2Range MX = get(K2_C_M, s_mx), MO1 = get(K2_C_M, s_o1);
+      K2Range MO2, I1E, D1E, I2E, D2E;
+      MO2.lo = I1E.lo = D1E.lo = I2E.lo = D2E.lo = 1;
+      MO2.hi = I1E.hi = D1E.hi = I2E.hi = D2E.hi = -1;
+      if (AFF) {
+        MO2 = get(K2_C_M, s_o2); I1E = get(K2_C_I1, s_e1); D1E = get(K2_C_D1, s_e1);
+        I2E = get(K2_C_I2, s_e2); D2E = get(K2_C_D2, s_e2);
+      }
+      int lo = INT_MAX, hi = INT_MIN;
+      if (s == 0) { lo = -pr.pbf; hi = pr.tbf; }
+      else {
+        if (MX.any()) { lo = min(lo, MX.lo); hi = max(hi, MX.hi); }
+        if (MO1.any()) { lo = min(lo, MO1.lo - 1); hi = max(hi, MO1.hi + 1); }
+        if (AFF) {
+          if (MO2.any()) { lo = min(lo, MO2.lo - 1); hi = max(hi, MO2.hi + 1); }
+          if (I1E.any()) { lo = min(lo, I1E.lo + 1); hi = max(hi, I1E.hi + 1); }
+          if (D1E.any()) { lo = min(lo, D1E.lo - 1); hi = max(hi, D1E.hi - 1); }
+          if (I2E.any()) { lo = min(lo, I2E.lo + 1); hi = max(hi, I2E.hi + 1); }
+          if (D2E.any()) { lo = min(lo, D2E.lo - 1); hi = max(hi, D2E.hi - 1); }
+        }
+      }
+      if (lo > hi) {  // wavefront s does not exist
+        if (tid == 0) {
+          meta[2 * slot_of(K2_C_M, s)] = 1; meta[2 * slot_of(K2_C_M, s) + 1] = -1;
+          if (AFF) {
+            for (int c = 1; c < 5; ++c) { meta[2 * slot_of(c, s)] = 1; meta[2 * slot_of(c, s) + 1] = -1; }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { last[c].lo = 1; last[c].hi = -1; }
+        __syncthreads();
+        continue;
+      }
+      const int width = hi - lo + 1;
+      if (bt_used + (unsigned long long)width > bt_cap) { res_status = -6; break; }
+      const bool has2 = AFF && (MO2.any() || I2E.any() || D2E.any());
+      // interior where every read of every (existing-piece) source is in range
+      int ilo, ihi;
+      {
+        bool ok = MX.any() && MO1.any();
+        ilo = max(MX.lo, MO1.lo + 1); ihi = min(MX.hi, MO1.hi - 1);
+        if (AFF) {
+          ok = ok && I1E.any() && D1E.any();
+          ilo = max(ilo, max(I1E.lo + 1, D1E.lo - 1)); ihi = min(ihi, min(I1E.hi + 1, D1E.hi - 1));
+          if (has2) {
+            ok = ok && MO2.any() && I2E.any() && D2E.any();
+            ilo = max(ilo, max(MO2.lo + 1, max(I2E.lo + 1, D2E.lo - 1)));
+            ihi = min(ihi, min(MO2.hi - 1, min(I2E.hi + 1, D2E.hi - 1)));
+          }
+        }
+        if (!ok || s == 0) { ilo = 1; ihi = 0; }
+      }
+      const int32_t* rMX = rings + (size_t)slot_of(K2_C_M, max(s_mx, 0)) * Wp + kbase;
+      const int32_t* rMO1 = rings + (size_t)slot_of(K2_C_M, max(s_o1, 0)) * Wp + kbase;
+      const int32_t* rMO2 = rings + (size_t)slot_of(K2_C_M, max(s_o2, 0)) * Wp + kbase;
+      const int32_t* rI1E = rings + (size_t)slot_of(K2_C_I1, max(s_e1, 0)) * Wp + kbase;
+      const int32_t* rD1E = rings + (size_t)slot_of(K2_C_D1, max(s_e1, 0)) * Wp + kbase;
+      const int32_t* rI2E = rings + (size_t)slot_of(K2_C_I2, max(s_e2, 0)) * Wp + kbase;
+      const int32_t* rD2E = rings + (size_t)slot_of(K2_C_D2, max(s_e2, 0)) * Wp + kbase;
+      int32_t* oM = rings + (size_t)slot_of(K2_C_M, s) * Wp + kbase;
+      int32_t* oI1 = rings + (size_t)slot_of(K2_C_I1, s) * Wp + kbase;
+      int32_t* oD1 = rings + (size_t)slot_of(K2_C_D1, s) * Wp + kbase;
+      int32_t* oI2 = rings + (size_t)slot_of(K2_C_I2, s) * Wp + kbase;
+      int32_t* oD2 = rings + (size_t)slot_of(K2_C_D2, s) * Wp + kbase;
+      unsigned char* btrow = bt + bt_used;
+      const int cMX = MX.cnt(), cMO1 = MO1.cnt(), cMO2 = MO2.cnt(), cI1E = I1E.cnt(), cD1E = D1E.cnt(),
+                cI2E = I2E.cnt(), cD2E = D2E.cnt();
+
+      int red[NRED];  // all as minima: [0] term_k, then (lo, -hi) per component
+#pragma unroll
+      for (int j = 0; j < NRED; ++j) red[j] = INT_MAX;
+
+      for (int kb = lo + warp * 32; kb <= hi; kb += NT) {
+        const int k = kb + lane;
+        const bool act = k <= hi;
+        int32_t best = WNULL, ins1 = WNULL, ins2 = WNULL, del1 = WNULL, del2 = WNULL;
+        uint32_t ch = 0;
+        if (s == 0) {
+          if (act) best = max(k, 0);
+        } else {
+          int32_t mx, i1o, d1o, i1e = WNULL, d1e = WNULL, i2o = WNULL, d2o = WNULL, i2e = WNULL, d2e = WNULL;
+          if (kb >= ilo && kb + 31 <= ihi) {
+            mx = rMX[k]; i1o = rMO1[k - 1]; d1o = rMO1[k + 1];
+            if (AFF) {
+              i1e = rI1E[k - 1]; d1e = rD1E[k + 1];
+              if (has2) { i2o = rMO2[k - 1]; d2o = rMO2[k + 1]; i2e = rI2E[k - 1]; d2e = rD2E[k + 1]; }
+            }
+          } else {
+            mx = k2_guard(rMX, k, MX.lo, cMX);
+            i1o = k2_guard(rMO1, k - 1, MO1.lo, cMO1);
+            d1o = k2_guard(rMO1, k + 1, MO1.lo, cMO1);
+            if (AFF) {
+              i1e = k2_guard(rI1E, k - 1, I1E.lo, cI1E);
+              d1e = k2_guard(rD1E, k + 1, D1E.lo, cD1E);
+              if (has2) {
+                i2o = k2_guard(rMO2, k - 1, MO2.lo, cMO2);
+                d2o = k2_guard(rMO2, k + 1, MO2.lo, cMO2);
+                i2e = k2_guard(rI2E, k - 1, I2E.lo, cI2E);
+                d2e = k2_guard(rD2E, k + 1, D2E.lo, cD2E);
+              }
+            }
+          }
+          const int32_t mis = mx + 1;
+          if (AFF) {
+            ins1 = max(i1o, i1e) + 1; if (i1e >= i1o) ch |= K2_BIT_I1E;
+            ins2 = max(i2o, i2e) + 1; if (i2e >= i2o) ch |= K2_BIT_I2E;
+            del1 = max(d1o, d1e);     if (d1e >= d1o) ch |= K2_BIT_D1E;
+            del2 = max(d2o, d2e);     if (d2e >= d2o) ch |= K2_BIT_D2E;
+            best = ins1; uint32_t sel = K2_SEL_I1;
+            if (ins2 >= best) { best = ins2; sel = K2_SEL_I2; }
+            if (del1 >= best) { best = del1; sel = K2_SEL_D1; }
+            if (del2 >= best) { best = del2; sel = K2_SEL_D2; }
+            if (mis >= best) { best = mis; sel = K2_SEL_X; }
+            ch |= sel;
+          } else {
+            const int32_t ins = i1o + 1, del = d1o;
+            best = ins; ch = K2_SEL_I1;
+            if (del >= best) { best = del; ch = K2_SEL_D1; }
+            if (mis >= best) { best = mis; ch = K2_SEL_X; }
+          }
+          if (!act) { best = WNULL; ins1 = ins2 = del1 = del2 = WNULL; }
+        }
+        if (!k2_in_matrix(best, k, plen, tlen)) best = WNULL;
+        // ---- extend M along matches ----
+        int off = best;
+        bool pending = false;
+        if (best >= 0) {
+          const int v = off - k;
+          uint32_t xw = window8(wp, v) ^ window8(wt, off);
+          if (xw) off += lead_eq(xw);
+          else {
+            off += 8;
+            xw = window8(wp, v + 8) ^ window8(wt, off);
+            if (xw) off += lead_eq(xw);
+            else { off += 8; pending = true; }
+          }
+        }
+        unsigned pm = __ballot_sync(FULL, pending);
+        while (pm) {
+          const int src = __ffs((int)pm) - 1;
+          pm &= pm - 1;
+          const int ko = __shfl_sync(FULL, k, src), ho = __shfl_sync(FULL, off, src);
+          const int adv = coop_extend(wp, wt, plen, tlen, ko, ho, lane);
+          if (lane == src) off += adv;
+        }
+        if (best >= 0) {
+          const int v = off - k;
+          if ((off >= tlen && plen - v <= pr.pef) || (v >= plen && tlen - off <= pr.tef)) red[0] = min(red[0], k);
+          red[1] = min(red[1], k); red[2] = min(red[2], -k);
+        }
+        if (act) {
+          oM[k] = best >= 0 ? off : WNULL;
+          if (s > 0) btrow[k - lo] = (unsigned char)ch;
+          if (AFF && s > 0) {
+            oI1[k] = ins1; oD1[k] = del1;
+            if (k2_in_matrix(ins1, k, plen, tlen)) { red[3] = min(red[3], k); red[4] = min(red[4], -k); }
+            if (k2_in_matrix(del1, k, plen, tlen)) { red[5] = min(red[5], k); red[6] = min(red[6], -k); }
+            if (has2) {
+              oI2[k] = ins2; oD2[k] = del2;
+              if (k2_in_matrix(ins2, k, plen, tlen)) { red[7] = min(red[7], k); red[8] = min(red[8], -k); }
+              if (k2_in_matrix(del2, k, plen, tlen)) { red[9] = min(red[9], k); red[10] = min(red[10], -k); }
+            }
+          }
+        }
+      }
+      // ---- block reduction: termination diagonal + trimmed ranges ----
+      int* pp = part + par * 32 * NRED;
+#pragma unroll
+      for (int j = 0; j < NRED; ++j) {
+        const int v = warp_min(red[j]);
+        if (lane == 0) pp[warp * NRED + j] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < NRED; ++j) red[j] = warp_min(lane < NW ? pp[lane * NRED + j] : INT_MAX);
+      par ^= 1;
+      K2Range now[5];
+#pragma unroll
+      for (int c = 0; c < 5; ++c) { now[c].lo = 1; now[c].hi = -1; }
+#pragma unroll
+      for (int c = 0; c < (AFF ? 5 : 1); ++c) {
+        const int l = red[1 + 2 * c], h = red[2 + 2 * c];
+        if (l != INT_MAX) { now[c].lo = l; now[c].hi = -h; }
+      }
+      if (tid == 0) {
+#pragma unroll
+        for (int c = 0; c < (AFF ? 5 : 1); ++c) {
+          const int sl = slot_of(c, s);
+          meta[2 * sl] = now[c].lo; meta[2 * sl + 1] = now[c].hi;
+        }
+        rowoff[s] = bt_used;
+        rowlo[s] = lo;
+        cells_acc += (unsigned long long)width;
+      }
+#pragma unroll
+      for (int c = 0; c < 5; ++c) last[c] = now[c];
+      if (s > 0) bt_used += (unsigned long long)width;
+      if (red[0] != INT_MAX) { end_k = red[0]; done = true; break; }
+    }
+
+    // ---- backtrace (warp 0): choice walk to score 0, then forward replay ----
+    if (done) {
+      __syncthreads();  // rowoff/rowlo/bt/oM of the last step visible to warp 0
+      if (warp == 0) {
+        const int32_t* oM = rings + (size_t)slot_of(K2_C_M, s) * Wp + kbase;
+        const int end_off = oM[end_k];
+        int k0 = 0, nb = 0, bad = 0;
+        if (lane == 0) {
+          int sc = s, k = end_k, comp = K2_C_M;
+          int last_code = -1;
+          uint32_t run = 0;
+          auto push = [&](int code) {
+            if (code == last_code) { ++run; return; }
+            if (run) { if ((size_t)nb < E_cap) tmp_b[nb++] = (run << 3) | (uint32_t)last_code; else bad = 1; }
+            last_code = code; run = 1;
+          };
+          while (sc > 0 && !bad) {
+            const uint32_t c = bt[rowoff[sc] + (unsigned long long)(k - rowlo[sc])];
+            if (!AFF) {
+              const uint32_t sel = c & 7u;
+              if (sel == K2_SEL_X) { push(K2_E_X); sc -= P.x; }
+              else if (sel == K2_SEL_I1) { push(K2_E_IO); sc -= P.e1; k -= 1; }
+              else { push(K2_E_DO); sc -= P.e1; k += 1; }
+              continue;
+            }
+            switch (comp) {
+              case K2_C_M: {
+                const uint32_t sel = c & 7u;
+                if (sel == K2_SEL_X) { push(K2_E_X); sc -= P.x; }
+                else if (sel == K2_SEL_I1) comp = K2_C_I1;
+                else if (sel == K2_SEL_I2) comp = K2_C_I2;
+                else if (sel == K2_SEL_D1) comp = K2_C_D1;
+                else comp = K2_C_D2;
+                break;
+              }
+              case K2_C_I1:
+                if (c & K2_BIT_I1E) { push(K2_E_IE); sc -= P.e1; } else { push(K2_E_IO); sc -= P.o1 + P.e1; comp = K2_C_M; }
+                k -= 1;
+                break;
+              case K2_C_I2:
+                if (c & K2_BIT_I2E) { push(K2_E_IE); sc -= P.e2; } else { push(K2_E_IO); sc -= P.o2 + P.e2; comp = K2_C_M; }
+                k -= 1;
+                break;
+              case K2_C_D1:
+                if (c & K2_BIT_D1E) { push(K2_E_DE); sc -= P.e1; } else { push(K2_E_DO); sc -= P.o1 + P.e1; comp = K2_C_M; }
+                k += 1;
+                break;
+              default:
+                if (c & K2_BIT_D2E) { push(K2_E_DE); sc -= P.e2; } else { push(K2_E_DO); sc -= P.o2 + P.e2; comp = K2_C_M; }
+                k += 1;
+                break;
+            }
+          }
+          if (run) { if ((size_t)nb < E_cap) tmp_b[nb++] = (run << 3) | (uint32_t)last_code; else bad = 1; }
+          if (sc != 0 || comp != K2_C_M) bad = 1;
+          k0 = k;
+        }
+        k0 = __shfl_sync(FULL, k0, 0);
+        nb = __shfl_sync(FULL, nb, 0);
+        bad = __shfl_sync(FULL, bad, 0);
+        __syncwarp();
+        const int h_end = end_off, v_end = end_off - end_k;
+        const int al_t = h_end - max(k0, 0), al_p = v_end - max(-k0, 0);
+        res_score = (P.match == 0) ? -s : ((-P.match) * (al_p + al_t) - s) / 2;
+        unsigned long long o_off = 0;
+        uint32_t o_len = 0;
+        if (P.want_cigar && !bad) {
+          // forward replay; lane 0 keeps the run-length output, all lanes extend matches together
+          int h = max(k0, 0), v = max(-k0, 0), nf = 0, cur_code = -1;
+          uint32_t cur_len = 0;
+          auto emit = [&](int code, uint32_t len) {
+            if (len == 0) return;
+            if (code == cur_code) { cur_len += len; return; }
+            if (cur_len && lane == 0) { if ((size_t)nf < E_cap) tmp_f[nf] = (cur_len << 2) | (uint32_t)cur_code; }
+            if (cur_len) ++nf;
+            cur_code = code; cur_len = len;
+          };
+          emit(2, (uint32_t)h);
+          emit(3, (uint32_t)v);
+          for (int i = nb - 1; i >= 0; --i) {
+            const uint32_t e = tmp_b[i];
+            const int code = (int)(e & 7u);
+            const uint32_t cnt = e >> 3;
+            if (code == K2_E_IE) { emit(2, cnt); h += (int)cnt; continue; }
+            if (code == K2_E_DE) { emit(3, cnt); v += (int)cnt; continue; }
+            for (uint32_t j = 0; j < cnt; ++j) {
+              const int m = coop_extend(wp, wt, plen, tlen, h - v, h, lane);
+              emit(0, (uint32_t)m); h += m; v += m;
+              if (code == K2_E_X) { emit(1, 1); ++h; ++v; }
+              else if (code == K2_E_IO) { emit(2, 1); ++h; }
+              else { emit(3, 1); ++v; }
+            }
+          }
+          {
+            const int m = coop_extend(wp, wt, plen, tlen, h - v, h, lane);
+            emit(0, (uint32_t)m); h += m; v += m;
+          }
+          if (h != h_end || v != v_end) bad = 1;
+          emit(2, (uint32_t)(tlen - h));
+          emit(3, (uint32_t)(plen - v));
+          emit(-2, 1);  // flush
+          if ((size_t)nf > E_cap) bad = 1;
+          if (!bad) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(P.pool_used, (unsigned long long)nf);
+            base = __shfl_sync(FULL, base, 0);
+            __syncwarp();
+            if (base + (unsigned long long)nf > P.pool_cap) { res_status = -4; }
+            else {
+              for (int i = lane; i < nf; i += 32) P.pool[base + i] = tmp_f[i];
+              o_off = base; o_len = (uint32_t)nf;
+            }
+          }
+        }
+        if (bad) res_status = -9;
+        if (lane == 0) { P.scores[pi] = res_score; P.status[pi] = res_status; P.out_off[pi] = o_off; P.out_len[pi] = o_len; }
+      }
+    } else if (tid == 0) {
+      P.scores[pi] = 0; P.status[pi] = res_status; P.out_off[pi] = 0; P.out_len[pi] = 0;
+    }
+  }
+  if (tid == 0 && cells_acc) atomicAdd(P.cells, cells_acc);
+}
+
+}  // namespace sfc

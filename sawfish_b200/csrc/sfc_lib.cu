@@ -1,0 +1,817 @@
+// sfc_lib.cu — host side of libsawfish_cuda.so: the C ABI declared in include/sawfish_cuda.h.
+//
+// One sfc_ctx owns one CUDA stream and every device buffer of one GPU.  A batch goes
+//   upload (H2D of the ASCII arena + pair table, K3 pack)  ->  run (K1 score-only / K2 backtrace kernels)
+//   ->  download (scores, status, run-length ops).
+// There is no CPU fallback anywhere in this file: if CUDA is unavailable every entry point fails.
+#include "../../include/sawfish_cuda.h"
+
+#include <algorithm>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sfc_device.cuh"
+#include "sfc_k_align.cuh"
+#include "sfc_k_pack.cuh"
+#include "sfc_k_score.cuh"
+
+using namespace sfc;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct AdjPen {
+  int metric, x, o1, e1, o2, e2, match;
+};
+
+}  // namespace
+
+struct sfc_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  std::string err;
+  size_t ws_limit = 0;
+  // device buffers
+  DevBuf d_arena, d_nib, d_seqs, d_seqwoff, d_pairs, d_order, d_scores, d_status, d_misc, d_pool, d_outoff, d_outlen, d_ws;
+  // batch state
+  size_t n_pairs = 0;
+  bool uploaded = false, ran = false;
+  int want_cigar = 0;
+  std::vector<DevPair> h_pairs;
+  std::vector<SeqDesc> h_seqs;
+  std::vector<uint32_t> h_seqwoff;
+  std::vector<uint32_t> h_order;
+  std::vector<int32_t> h_status;
+  std::vector<unsigned long long> h_outoff;
+  std::vector<uint32_t> h_outlen;
+  std::vector<uint32_t> h_pool;
+  unsigned long long pool_used = 0;
+  sfc_batch_stats stats = {};
+};
+
+struct sfc_aligner {
+  sfc_ctx* ctx;
+  sfc_penalties pen;
+  std::vector<uint8_t> text;
+};
+
+namespace {
+
+int fail(sfc_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    c->err = buf;
+  }
+  return code;
+}
+
+#define CU(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) return fail(c, SFC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+int ensure(sfc_ctx* c, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return 0;
+  if (b.p) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&b.p, want);
+  }
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    return fail(c, SFC_ERR_OOM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+  }
+  b.cap = want;
+  return 0;
+}
+
+void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+int adjust_penalties(const sfc_penalties* pen, AdjPen* a) {
+  if (!pen || (pen->metric != 0 && pen->metric != 1) || pen->match > 0) return -1;
+  const int m = pen->match;
+  a->metric = pen->metric;
+  a->match = m;
+  if (m == 0) {
+    a->x = pen->mismatch; a->o1 = pen->gap_open1; a->e1 = pen->gap_ext1; a->o2 = pen->gap_open2; a->e2 = pen->gap_ext2;
+  } else {  // Eizenga's adjustment, as WFA2-lib applies it for match < 0
+    a->x = 2 * pen->mismatch - 2 * m;
+    a->o1 = 2 * pen->gap_open1; a->e1 = 2 * pen->gap_ext1 - m;
+    a->o2 = 2 * pen->gap_open2; a->e2 = 2 * pen->gap_ext2 - m;
+  }
+  if (a->metric == 0) { a->o1 = 0; a->o2 = 0; a->e2 = 0; }
+  if (a->x <= 0 || a->e1 <= 0) return -1;
+  if (a->metric == 1 && (a->e2 <= 0 || a->o1 < 0 || a->o2 < 0)) return -1;
+  if (a->x > 4096 || a->o1 + a->e1 > 4096 || a->o2 + a->e2 > 4096) return -1;
+  return 0;
+}
+
+long long gap_cost(const AdjPen& a, long long L) {
+  if (L <= 0) return 0;
+  if (a.metric == 0) return (long long)a.e1 * L;
+  return std::min((long long)a.o1 + (long long)a.e1 * L, (long long)a.o2 + (long long)a.e2 * L);
+}
+
+void init_lut_host(uint8_t* lut) {
+  memset(lut, 0xFF, 256);
+  const char* up = "ACGTN";
+  const char* lo = "acgtn";
+  for (int i = 0; i < 5; ++i) { lut[(uint8_t)up[i]] = (uint8_t)i; lut[(uint8_t)lo[i]] = (uint8_t)(5 + i); }
+}
+
+// ---- K1 size classes (shared-memory ring) ----
+struct K1Class { int wcap; int wpp; };
+const K1Class kK1Classes[] = {{640, 2}, {1152, 4}, {2304, 8}, {4352, 8}};
+constexpr int kNumK1Classes = 4;
+
+template <int WPP>
+int launch_k1(sfc_ctx* c, const K1Params& P, int groups_per_block, int grid, size_t smem) {
+  CU(cudaFuncSetAttribute(k1_score<WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k1_score<WPP><<<grid, groups_per_block * WPP * 32, smem, c->stream>>>(P);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+__global__ void int_peak_kernel(unsigned* out, int iters, unsigned seed) {
+  unsigned a0 = threadIdx.x + seed, a1 = a0 * 3u + 1u, a2 = a0 * 5u + 2u, a3 = a0 * 7u + 3u;
+  unsigned a4 = a0 ^ 0x9E3779B9u, a5 = a1 ^ 0x7F4A7C15u, a6 = a2 ^ 0x85EBCA6Bu, a7 = a3 ^ 0xC2B2AE35u;
+  const unsigned b = blockIdx.x | 1u, d = seed | 3u;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {  // 8 chains x 8 x (IADD + LOP3) per iteration
+      a0 = (a0 + b) ^ d; a1 = (a1 + b) ^ d; a2 = (a2 + b) ^ d; a3 = (a3 + b) ^ d;
+      a4 = (a4 + b) ^ d; a5 = (a5 + b) ^ d; a6 = (a6 + b) ^ d; a7 = (a7 + b) ^ d;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
+}  // namespace
+
+// ============================================================================ context
+extern "C" int sfc_abi_version(void) { return SFC_ABI_VERSION; }
+
+extern "C" int sfc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" int sfc_create(int device_ordinal, sfc_ctx** out) {
+  if (!out) return SFC_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); return SFC_ERR_NO_DEVICE; }
+  if (device_ordinal < 0 || device_ordinal >= n) return SFC_ERR_INVALID;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) return SFC_ERR_NO_DEVICE;
+  if (prop.major != 10) return SFC_ERR_NO_DEVICE;  // built for sm_100a only
+  sfc_ctx* c = new (std::nothrow) sfc_ctx();
+  if (!c) return SFC_ERR_OOM;
+  c->device = device_ordinal;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cudaSetDevice(device_ordinal) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return SFC_ERR_CUDA;
+  }
+  for (auto& e : c->ev) {
+    if (cudaEventCreate(&e) != cudaSuccess) { sfc_destroy(c); return SFC_ERR_CUDA; }
+  }
+  uint8_t lut[256];
+  init_lut_host(lut);
+  if (cudaMemcpyToSymbol(c_nib_lut, lut, 256) != cudaSuccess) { sfc_destroy(c); return SFC_ERR_CUDA; }
+  *out = c;
+  return SFC_OK;
+}
+
+extern "C" void sfc_destroy(sfc_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (DevBuf* b : {&c->d_arena, &c->d_nib, &c->d_seqs, &c->d_seqwoff, &c->d_pairs, &c->d_order, &c->d_scores, &c->d_status,
+                    &c->d_misc, &c->d_pool, &c->d_outoff, &c->d_outlen, &c->d_ws})
+    release(*b);
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" const char* sfc_last_error(const sfc_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+extern "C" int sfc_set_workspace_limit(sfc_ctx* c, size_t bytes) {
+  if (!c) return SFC_ERR_INVALID;
+  c->ws_limit = bytes;
+  return SFC_OK;
+}
+
+// ============================================================================ upload
+extern "C" int sfc_batch_upload(sfc_ctx* c, const uint8_t* arena, size_t arena_len, const sfc_pair* pairs, size_t n) {
+  if (!c) return SFC_ERR_INVALID;
+  if (!arena || !pairs || n == 0 || n > 0x7FFFFFF0u) return fail(c, SFC_ERR_INVALID, "null/empty batch");
+  CU(cudaSetDevice(c->device));
+  c->uploaded = c->ran = false;
+  c->n_pairs = n;
+  c->h_pairs.resize(n);
+  c->h_seqs.resize(2 * n);
+  c->h_seqwoff.resize(2 * n + 1);
+  uint64_t woff = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const sfc_pair& p = pairs[i];
+    if (p.pattern_len == 0 || p.text_len == 0) return fail(c, SFC_ERR_INVALID, "pair %zu: empty sequence", i);
+    if (p.pattern_len > 0x3FFFFFFFu || p.text_len > 0x3FFFFFFFu) return fail(c, SFC_ERR_INVALID, "pair %zu: sequence too long", i);
+    if (p.pattern_off + p.pattern_len > arena_len || p.text_off + p.text_len > arena_len)
+      return fail(c, SFC_ERR_INVALID, "pair %zu: sequence outside arena", i);
+    if (p.pattern_begin_free < 0 || p.pattern_end_free < 0 || p.text_begin_free < 0 || p.text_end_free < 0 ||
+        (uint32_t)p.pattern_begin_free > p.pattern_len || (uint32_t)p.pattern_end_free > p.pattern_len ||
+        (uint32_t)p.text_begin_free > p.text_len || (uint32_t)p.text_end_free > p.text_len)
+      return fail(c, SFC_ERR_INVALID, "pair %zu: ends-free allowance outside [0, len]", i);
+    const uint32_t rev = (p.flags & SFC_PAIR_REVERSE) ? 1u : 0u;
+    DevPair& d = c->h_pairs[i];
+    d.plen = (int32_t)p.pattern_len; d.tlen = (int32_t)p.text_len;
+    d.pbf = p.pattern_begin_free; d.pef = p.pattern_end_free; d.tbf = p.text_begin_free; d.tef = p.text_end_free;
+    c->h_seqs[2 * i] = SeqDesc{p.pattern_off, p.pattern_len, rev};
+    c->h_seqwoff[2 * i] = (uint32_t)woff; d.p_woff = (uint32_t)woff;
+    woff += (p.pattern_len + 7) / 8 + 2;
+    c->h_seqs[2 * i + 1] = SeqDesc{p.text_off, p.text_len, rev | 2u};
+    c->h_seqwoff[2 * i + 1] = (uint32_t)woff; d.t_woff = (uint32_t)woff;
+    woff += (p.text_len + 7) / 8 + 2;
+    if (woff > 0xFFFFFFF0ull) return fail(c, SFC_ERR_INVALID, "batch too large (packed arena exceeds 2^32 words)");
+  }
+  c->h_seqwoff[2 * n] = (uint32_t)woff;
+  int rc;
+  if ((rc = ensure(c, c->d_arena, arena_len))) return rc;
+  if ((rc = ensure(c, c->d_nib, (size_t)woff * 4))) return rc;
+  if ((rc = ensure(c, c->d_seqs, 2 * n * sizeof(SeqDesc)))) return rc;
+  if ((rc = ensure(c, c->d_seqwoff, (2 * n + 1) * 4))) return rc;
+  if ((rc = ensure(c, c->d_pairs, n * sizeof(DevPair)))) return rc;
+  if ((rc = ensure(c, c->d_misc, 256))) return rc;
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  CU(cudaMemcpyAsync(c->d_arena.p, arena, arena_len, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_seqs.p, c->h_seqs.data(), 2 * n * sizeof(SeqDesc), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_seqwoff.p, c->h_seqwoff.data(), (2 * n + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_pairs.p, c->h_pairs.data(), n * sizeof(DevPair), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(c->d_misc.p, 0, 256, c->stream));
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  {
+    const uint32_t total_words = (uint32_t)woff;
+    const int grid = (int)std::min<uint64_t>((total_words + 255) / 256, (uint64_t)c->sm_count * 16);
+    k3_pack<<<grid, 256, 0, c->stream>>>((const uint8_t*)c->d_arena.p, (const SeqDesc*)c->d_seqs.p, (const uint32_t*)c->d_seqwoff.p,
+                                         (uint32_t)(2 * n), total_words, (uint32_t*)c->d_nib.p, (uint32_t*)c->d_misc.p + 32);
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(c->ev[2], c->stream));
+  c->stats = sfc_batch_stats{};
+  c->stats.h2d_bytes = arena_len + 2 * n * sizeof(SeqDesc) + (2 * n + 1) * 4 + n * sizeof(DevPair);
+  c->stats.launches = 1;
+  c->uploaded = true;
+  return SFC_OK;
+}
+
+// ============================================================================ run
+// d_misc layout (uint32 words): [0] K1 work counter, [2..3] cells (u64), [4..5] pool_used (u64),
+// [8] K2 work counter, [32] bad-symbol flag.
+extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_cigar) {
+  if (!c) return SFC_ERR_INVALID;
+  if (!c->uploaded) return fail(c, SFC_ERR_INVALID, "sfc_batch_run before sfc_batch_upload");
+  AdjPen a;
+  if (adjust_penalties(pen, &a)) return fail(c, SFC_ERR_INVALID, "invalid penalties");
+  CU(cudaSetDevice(c->device));
+  const size_t n = c->n_pairs;
+  int rc;
+  if ((rc = ensure(c, c->d_scores, n * 4))) return rc;
+  if ((rc = ensure(c, c->d_status, n * 4))) return rc;
+  if ((rc = ensure(c, c->d_order, n * 4))) return rc;
+  if ((rc = ensure(c, c->d_outoff, n * 8))) return rc;
+  if ((rc = ensure(c, c->d_outlen, n * 4))) return rc;
+  c->want_cigar = want_cigar ? 1 : 0;
+
+  // ---- classify pairs ----
+  const int lookL = std::max(a.x, a.e1);
+  std::vector<uint32_t> k1_lists[kNumK1Classes];
+  std::vector<uint32_t> k2_small, k2_large;
+  for (size_t i = 0; i < n; ++i) {
+    const DevPair& d = c->h_pairs[i];
+    const long long W = (long long)d.plen + d.tlen + 5;
+    bool k1 = (a.metric == 0) && !want_cigar && d.plen <= K1_MAX_LEN && d.tlen <= K1_MAX_LEN && d.pbf <= K1_MAX_FREE &&
+              d.tbf <= K1_MAX_FREE && lookL <= 32;
+    if (k1) {
+      int cls = -1;
+      for (int j = 0; j < kNumK1Classes; ++j) if (W <= kK1Classes[j].wcap) { cls = j; break; }
+      if (cls >= 0) { k1_lists[cls].push_back((uint32_t)i); continue; }
+    }
+    if (W <= 4096) k2_small.push_back((uint32_t)i); else k2_large.push_back((uint32_t)i);
+  }
+  auto sort_heavy_first = [&](std::vector<uint32_t>& v) {
+    std::stable_sort(v.begin(), v.end(), [&](uint32_t x, uint32_t y) {
+      const long long wx = (long long)c->h_pairs[x].plen + c->h_pairs[x].tlen, wy = (long long)c->h_pairs[y].plen + c->h_pairs[y].tlen;
+      return (wx >> 6) > (wy >> 6);
+    });
+  };
+  c->h_order.clear();
+  size_t k1_begin[kNumK1Classes + 1];
+  for (int j = 0; j < kNumK1Classes; ++j) {
+    sort_heavy_first(k1_lists[j]);
+    k1_begin[j] = c->h_order.size();
+    c->h_order.insert(c->h_order.end(), k1_lists[j].begin(), k1_lists[j].end());
+  }
+  k1_begin[kNumK1Classes] = c->h_order.size();
+  sort_heavy_first(k2_small);
+  sort_heavy_first(k2_large);
+  const size_t k2s_begin = c->h_order.size();
+  c->h_order.insert(c->h_order.end(), k2_small.begin(), k2_small.end());
+  const size_t k2l_begin = c->h_order.size();
+  c->h_order.insert(c->h_order.end(), k2_large.begin(), k2_large.end());
+  c->stats.n_score_kernel = (uint32_t)k2s_begin;
+  c->stats.n_align_kernel = (uint32_t)(n - k2s_begin);
+
+  uint32_t* misc = (uint32_t*)c->d_misc.p;
+  CU(cudaEventRecord(c->ev[3], c->stream));
+  CU(cudaMemcpyAsync(c->d_order.p, c->h_order.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(misc, 0, 64, c->stream));  // counters, cells, pool_used (not the bad-symbol flag)
+  c->stats.h2d_bytes += n * 4;
+
+  // ---- K1 launches ----
+  for (int j = 0; j < kNumK1Classes; ++j) {
+    const size_t cnt = k1_begin[j + 1] - k1_begin[j];
+    if (!cnt) continue;
+    const int wcap = kK1Classes[j].wcap;
+    int wpp = kK1Classes[j].wpp;
+    if (const char* e = getenv("SFC_K1_WPP")) {  // tuning knob: warps cooperating on one pair
+      const int v = atoi(e);
+      if (v == 1 || v == 2 || v == 4 || v == 8) wpp = v;
+    }
+    K1Params P;
+    P.pairs = (const DevPair*)c->d_pairs.p;
+    P.order = (const uint32_t*)c->d_order.p + k1_begin[j];
+    P.n = (uint32_t)cnt;
+    P.nib = (const uint32_t*)c->d_nib.p;
+    P.scores = (int32_t*)c->d_scores.p;
+    P.status = (int32_t*)c->d_status.p;
+    P.x = a.x; P.ip = a.e1; P.match = a.match;
+    P.rd = lookL + 1;
+    P.wcap = wcap;
+    P.win_cap = (wcap >> 3) + 4;
+    P.max_score = INT_MAX / 4;
+    P.cells = (unsigned long long*)(misc + 2);
+    size_t gb = (size_t)P.rd * wcap * 4 + (size_t)2 * P.win_cap * 8 + (size_t)(2 * P.rd + 2 * wpp * 3 + 2) * 4;
+    gb = (gb + 15) & ~(size_t)15;
+    P.group_bytes = (int)gb;
+    const size_t smem_max = c->smem_optin;
+    int max_groups = (int)(smem_max / gb);
+    if (max_groups < 1) return fail(c, SFC_ERR_UNSUPPORTED, "K1 class needs %zu B shared memory", gb);
+    int gpb = (wpp >= 2) ? 1 : std::min(max_groups, 256 / (wpp * 32));  // one group per block unless warp-per-pair
+    gpb = std::min(gpb, 15);
+    // prefer two resident blocks per SM when a block would otherwise monopolise shared memory with few warps
+    const size_t smem = gb * gpb;
+    const int blocks_per_sm = std::max(1, (int)((smem_max + 1024) / (smem + 1024)));
+    const size_t need_groups = cnt;
+    int grid = (int)std::min<size_t>((need_groups + gpb - 1) / gpb, (size_t)c->sm_count * blocks_per_sm);
+    // each class needs its own work counter value 0: reuse misc[0] sequentially via a memset between launches
+    CU(cudaMemsetAsync(misc, 0, 4, c->stream));
+    P.counter = misc;
+    switch (wpp) {
+      case 1: rc = launch_k1<1>(c, P, gpb, grid, smem); break;
+      case 2: rc = launch_k1<2>(c, P, gpb, grid, smem); break;
+      case 4: rc = launch_k1<4>(c, P, gpb, grid, smem); break;
+      default: rc = launch_k1<8>(c, P, gpb, grid, smem); break;
+    }
+    if (rc) return rc;
+    c->stats.launches++;
+  }
+
+  // ---- K2 launches (with workspace escalation) ----
+  c->pool_used = 0;
+  if (k2s_begin < n) {
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    size_t avail = (size_t)((double)(free_b + c->d_ws.cap + c->d_pool.cap) * 0.85);
+    if (c->ws_limit && avail > c->ws_limit) avail = c->ws_limit;
+    // output pool
+    size_t pool_cap = want_cigar ? std::max<size_t>((n - k2s_begin) * 64, (size_t)1 << 20) : 16;
+    if ((rc = ensure(c, c->d_pool, pool_cap * 4))) return rc;
+    pool_cap = c->d_pool.cap / 4;
+    const int nM = (a.metric == 1 ? std::max(a.x, std::max(a.o1 + a.e1, a.o2 + a.e2)) : lookL) + 1;
+    const int nG1 = a.e1 + 1, nG2 = a.e2 + 1;
+    const int nslots = a.metric == 1 ? nM + 2 * nG1 + 2 * nG2 : nM;
+    const int nred = a.metric == 1 ? 11 : 3;
+
+    struct Job { size_t begin, count; int threads; };
+    Job jobs[2] = {{k2s_begin, k2l_begin - k2s_begin, 128}, {k2l_begin, n - k2l_begin, 512}};
+    std::vector<uint32_t> retry;
+    for (int jj = 0; jj < 2; ++jj) {
+      Job job = jobs[jj];
+      if (!job.count) continue;
+      const uint32_t* order_host = c->h_order.data() + job.begin;
+      const uint32_t* order_dev = (const uint32_t*)c->d_order.p + job.begin;
+      size_t count = job.count;
+      int divisor = 1;
+      for (int pass = 0; pass < 12; ++pass) {
+        // fixed workspace need and shared-memory need of the heaviest pair in this pass
+        size_t max_fixed = 0, max_win = 0, max_W = 0;
+        for (size_t q = 0; q < count; ++q) {
+          const DevPair& d = c->h_pairs[order_host[q]];
+          const size_t Wp = (size_t)d.plen + d.tlen + 5;
+          long long scap = gap_cost(a, d.plen) + gap_cost(a, d.tlen) + 1;
+          scap = std::min<long long>(scap, INT_MAX / 4);
+          const size_t fixed = (size_t)nslots * Wp * 4 + ((size_t)scap + 1) * 12 + 2 * (((size_t)d.plen + d.tlen + 8) * 4) + 256;
+          max_fixed = std::max(max_fixed, fixed);
+          max_win = std::max(max_win, (size_t)(d.plen >> 3) + (d.tlen >> 3) + 2);
+          max_W = std::max(max_W, Wp);
+        }
+        const size_t smem = max_win * 8 + (size_t)nslots * 8 + (size_t)2 * 32 * nred * 4 + 64;
+        if (smem > c->smem_optin) {
+          // sequences do not fit shared memory: report per-pair status from the kernel (win_cap check) with a capped size
+        }
+        const size_t smem_use = std::min(smem, c->smem_optin);
+        const int win_cap = (int)((smem_use - (size_t)nslots * 8 - (size_t)2 * 32 * nred * 4 - 64) / 8);
+        int occ = 1;
+        if (a.metric == 1) {
+          CU(cudaFuncSetAttribute(k2_align<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_use));
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_align<true>, job.threads, smem_use));
+        } else {
+          CU(cudaFuncSetAttribute(k2_align<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_use));
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_align<false>, job.threads, smem_use));
+        }
+        occ = std::max(1, occ);
+        size_t n_cta = std::min<size_t>(count, (size_t)c->sm_count * occ);
+        n_cta = std::max<size_t>(1, n_cta / divisor);
+        // choice-byte budget: a few thousand score rows of the widest pair, escalated on retry
+        size_t bt_want = std::min<size_t>(std::max<size_t>((size_t)2048 * max_W * divisor, (size_t)4 << 20), (size_t)8 << 30);
+        size_t slab = max_fixed + bt_want;
+        while (n_cta > 1 && slab * n_cta > avail) n_cta = (n_cta + 1) / 2;
+        if (slab * n_cta > avail) slab = avail;
+        if (slab < max_fixed + 4096) return fail(c, SFC_ERR_OOM, "device workspace too small: need %zu B for one pair", max_fixed);
+        slab &= ~(size_t)255;
+        if ((rc = ensure(c, c->d_ws, slab * n_cta))) return rc;
+        K2Params P;
+        P.pairs = (const DevPair*)c->d_pairs.p;
+        P.order = order_dev;
+        P.n = (uint32_t)count;
+        P.counter = misc + 8;
+        P.nib = (const uint32_t*)c->d_nib.p;
+        P.scores = (int32_t*)c->d_scores.p;
+        P.status = (int32_t*)c->d_status.p;
+        P.metric = a.metric; P.x = a.x; P.o1 = a.o1; P.e1 = a.e1; P.o2 = a.o2; P.e2 = a.e2; P.match = a.match;
+        P.nM = nM; P.nG1 = nG1; P.nG2 = nG2;
+        P.slabs = (unsigned char*)c->d_ws.p;
+        P.slab_bytes = slab;
+        P.want_cigar = c->want_cigar;
+        P.pool = (uint32_t*)c->d_pool.p;
+        P.pool_cap = pool_cap;
+        P.pool_used = (unsigned long long*)(misc + 4);
+        P.out_off = (unsigned long long*)c->d_outoff.p;
+        P.out_len = (uint32_t*)c->d_outlen.p;
+        P.cells = (unsigned long long*)(misc + 2);
+        P.win_cap = win_cap;
+        P.max_score = INT_MAX / 4;
+        CU(cudaMemsetAsync(misc + 8, 0, 4, c->stream));
+        if (a.metric == 1) k2_align<true><<<(int)n_cta, job.threads, smem_use, c->stream>>>(P);
+        else k2_align<false><<<(int)n_cta, job.threads, smem_use, c->stream>>>(P);
+        CU(cudaGetLastError());
+        c->stats.launches++;
+        // ---- look for pairs that ran out of slab (-6) or of pool (-4) ----
+        c->h_status.resize(n);
+        CU(cudaMemcpyAsync(c->h_status.data(), c->d_status.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        retry.clear();
+        bool pool_short = false;
+        for (size_t q = 0; q < count; ++q) {
+          const int st = c->h_status[order_host[q]];
+          if (st == SFC_STATUS_OOM) retry.push_back(order_host[q]);
+          else if (st == -4) { retry.push_back(order_host[q]); pool_short = true; }
+        }
+        if (retry.empty()) break;
+        if (n_cta == 1 && slab >= avail - 4096 && !pool_short) break;  // nothing left to escalate: statuses stay -6
+        c->stats.retries++;
+        if (pool_short) {
+          // keep what is already in the pool, grow it for the rest
+          unsigned long long used = 0;
+          CU(cudaMemcpy(&used, misc + 4, 8, cudaMemcpyDeviceToHost));
+          DevBuf bigger;
+          size_t new_cap = std::max<size_t>(pool_cap * 4, (size_t)used + ((size_t)1 << 22));
+          if ((rc = ensure(c, bigger, new_cap * 4))) return rc;
+          CU(cudaMemcpy(bigger.p, c->d_pool.p, std::min<size_t>((size_t)used, pool_cap) * 4, cudaMemcpyDeviceToDevice));
+          // pool_used may have overshot the old capacity: reset it to the last valid fill level
+          // (entries are only written when they fit, so every recorded out_off/out_len is below pool_cap)
+          release(c->d_pool);
+          c->d_pool = bigger;
+          pool_cap = c->d_pool.cap / 4;
+          // the overshoot (failed reservations) leaves holes but never overlaps valid data
+        }
+        divisor *= 4;
+        // retry list becomes the new order (reuse the tail of d_order belonging to this job)
+        CU(cudaMemcpyAsync((uint32_t*)c->d_order.p + job.begin, retry.data(), retry.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        std::copy(retry.begin(), retry.end(), c->h_order.begin() + job.begin);
+        count = retry.size();
+      }
+    }
+  }
+  CU(cudaEventRecord(c->ev[4], c->stream));
+  c->ran = true;
+  return SFC_OK;
+}
+
+// ============================================================================ download
+extern "C" int sfc_batch_download(sfc_ctx* c, int32_t* scores, int32_t* status, uint32_t* ops_rle, size_t ops_cap, uint64_t* ops_off) {
+  if (!c) return SFC_ERR_INVALID;
+  if (!c->ran) return fail(c, SFC_ERR_INVALID, "sfc_batch_download before sfc_batch_run");
+  if (!scores || !status) return fail(c, SFC_ERR_INVALID, "null output");
+  if (c->want_cigar && (!ops_off || (!ops_rle && ops_cap))) return fail(c, SFC_ERR_INVALID, "null ops output");
+  CU(cudaSetDevice(c->device));
+  const size_t n = c->n_pairs;
+  uint32_t* misc = (uint32_t*)c->d_misc.p;
+  uint32_t h_misc[64];
+  CU(cudaEventRecord(c->ev[5], c->stream));
+  CU(cudaMemcpyAsync(scores, c->d_scores.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(status, c->d_status.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(h_misc, misc, 256, cudaMemcpyDeviceToHost, c->stream));
+  c->stats.d2h_bytes = n * 8 + 256;
+  const bool k2_any = c->stats.n_align_kernel > 0;
+  if (c->want_cigar && k2_any) {
+    c->h_outoff.resize(n);
+    c->h_outlen.resize(n);
+    CU(cudaMemcpyAsync(c->h_outoff.data(), c->d_outoff.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_outlen.data(), c->d_outlen.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2h_bytes += n * 12;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  unsigned long long cells, pool_used;
+  memcpy(&cells, h_misc + 2, 8);
+  memcpy(&pool_used, h_misc + 4, 8);
+  c->stats.cells = cells;
+  if (h_misc[32]) return fail(c, SFC_ERR_UNSUPPORTED, "sequence symbol outside {A,C,G,T,N,a,c,g,t,n}");
+  int ret = SFC_OK;
+  if (c->want_cigar) {
+    if (!k2_any) return fail(c, SFC_ERR_INVALID, "internal: cigar requested but no backtrace kernel ran");
+    const size_t pool_valid = std::min<size_t>((size_t)pool_used, c->d_pool.cap / 4);
+    c->h_pool.resize(pool_valid);
+    if (pool_valid) {
+      CU(cudaMemcpyAsync(c->h_pool.data(), c->d_pool.p, pool_valid * 4, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      c->stats.d2h_bytes += pool_valid * 4;
+    }
+    uint64_t acc = 0;
+    for (size_t i = 0; i < n; ++i) { ops_off[i] = acc; acc += (status[i] == 0) ? c->h_outlen[i] : 0; }
+    ops_off[n] = acc;
+    if (acc > ops_cap) ret = fail(c, SFC_ERR_CAPACITY, "ops buffer too small: need %llu entries", (unsigned long long)acc);
+    else {
+      for (size_t i = 0; i < n; ++i) {
+        if (status[i] != 0 || !c->h_outlen[i]) continue;
+        memcpy(ops_rle + ops_off[i], c->h_pool.data() + c->h_outoff[i], (size_t)c->h_outlen[i] * 4);
+      }
+    }
+  }
+  CU(cudaEventRecord(c->ev[6], c->stream));
+  CU(cudaEventSynchronize(c->ev[6]));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats.h2d_ms = ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->stats.pack_ms = ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stats.kernel_ms = ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6])); c->stats.d2h_ms = ms;
+  return ret;
+}
+
+extern "C" int sfc_batch_get_stats(const sfc_ctx* c, sfc_batch_stats* out) {
+  if (!c || !out) return SFC_ERR_INVALID;
+  *out = c->stats;
+  return SFC_OK;
+}
+
+extern "C" int sfc_align_batch(sfc_ctx* c, const sfc_penalties* pen, const uint8_t* arena, size_t arena_len, const sfc_pair* pairs,
+                               size_t n, int want_cigar, int32_t* scores, int32_t* status, uint32_t* ops_rle, size_t ops_cap,
+                               uint64_t* ops_off) {
+  int rc = sfc_batch_upload(c, arena, arena_len, pairs, n);
+  if (rc) return rc;
+  rc = sfc_batch_run(c, pen, want_cigar);
+  if (rc) return rc;
+  return sfc_batch_download(c, scores, status, ops_rle, ops_cap, ops_off);
+}
+
+// ============================================================================ CIGAR helpers (host)
+extern "C" int64_t sfc_expand_ops(const uint32_t* ops_rle, size_t n_runs, uint8_t* wfa_ops, size_t cap) {
+  static const char kOp[4] = {'M', 'X', 'I', 'D'};
+  size_t pos = 0;
+  for (size_t i = 0; i < n_runs; ++i) {
+    const size_t len = ops_rle[i] >> 2;
+    if (pos + len > cap) return SFC_ERR_CAPACITY;
+    memset(wfa_ops + pos, kOp[ops_rle[i] & 3u], len);
+    pos += len;
+  }
+  return (int64_t)pos;
+}
+
+namespace {
+// State machine of process_wfa2_cigar_string (reference src/wfa2_utils.rs:13-95), fed run by run in REVERSE op order.
+struct Translator {
+  int first_match = 0;
+  int64_t ref_offset = 0;
+  uint32_t* cigar;
+  size_t cap, n = 0;
+  uint8_t last = 0;
+  uint64_t count = 0;
+  int err = 0;
+  void flush(bool final_state) {
+    if (!count) return;
+    int op = -1;
+    switch (last) {
+      case 'M': op = 7; break;  // Equal
+      case 'X': op = 8; break;  // Diff
+      case 'D': op = (!first_match || final_state) ? 4 : 1; break;  // SoftClip : Ins
+      case 'I':
+        if (!first_match) ref_offset += (int64_t)count;
+        else if (!final_state) op = 2;  // Del
+        break;
+      default: err = SFC_ERR_INVALID; return;
+    }
+    if (op >= 0) {
+      if (n >= cap) { err = SFC_ERR_CAPACITY; return; }
+      cigar[n++] = (uint32_t)(count << 4) | (uint32_t)op;
+    }
+  }
+  void feed(uint8_t state, uint64_t len) {
+    if (!len) return;
+    if (state != last) { flush(false); count = 0; }
+    // first_al_match is raised by the first M/X *before* its own run is flushed, exactly as in the reference
+    if (!first_match && (state == 'M' || state == 'X')) first_match = 1;
+    count += len;
+    last = state;
+  }
+  void finish() { flush(true); count = 0; }
+};
+}  // namespace
+
+extern "C" int sfc_translate_cigar(const uint8_t* wfa_ops, size_t n_ops, int64_t* ref_offset, uint32_t* cigar, size_t cigar_cap,
+                                   size_t* n_cigar, int* has_match) {
+  if ((!wfa_ops && n_ops) || (!cigar && cigar_cap)) return SFC_ERR_INVALID;
+  Translator t;
+  t.cigar = cigar;
+  t.cap = cigar_cap;
+  for (size_t i = n_ops; i-- > 0;) {
+    const uint8_t s = wfa_ops[i];
+    if (s != 'M' && s != 'X' && s != 'I' && s != 'D') return SFC_ERR_INVALID;
+    t.feed(s, 1);
+    if (t.err) return t.err;
+  }
+  t.finish();
+  if (t.err) return t.err;
+  if (ref_offset) *ref_offset = t.ref_offset;
+  if (n_cigar) *n_cigar = t.n;
+  if (has_match) *has_match = t.first_match;
+  return SFC_OK;
+}
+
+extern "C" int sfc_translate_rle(const uint32_t* ops_rle, size_t n_runs, int64_t* ref_offset, uint32_t* cigar, size_t cigar_cap,
+                                 size_t* n_cigar, int* has_match) {
+  static const uint8_t kOp[4] = {'M', 'X', 'I', 'D'};
+  if ((!ops_rle && n_runs) || (!cigar && cigar_cap)) return SFC_ERR_INVALID;
+  Translator t;
+  t.cigar = cigar;
+  t.cap = cigar_cap;
+  for (size_t i = n_runs; i-- > 0;) {
+    t.feed(kOp[ops_rle[i] & 3u], ops_rle[i] >> 2);
+    if (t.err) return t.err;
+  }
+  t.finish();
+  if (t.err) return t.err;
+  if (ref_offset) *ref_offset = t.ref_offset;
+  if (n_cigar) *n_cigar = t.n;
+  if (has_match) *has_match = t.first_match;
+  return SFC_OK;
+}
+
+// ============================================================================ PairwiseAligner mirror
+static int aligner_new(sfc_ctx* c, const sfc_penalties& pen, sfc_aligner** out) {
+  if (!c || !out) return SFC_ERR_INVALID;
+  sfc_aligner* a = new (std::nothrow) sfc_aligner();
+  if (!a) return SFC_ERR_OOM;
+  a->ctx = c;
+  a->pen = pen;
+  *out = a;
+  return SFC_OK;
+}
+
+extern "C" int sfc_aligner_new_consensus(sfc_ctx* c, sfc_aligner** out) {
+  const sfc_penalties pen = {0, -1, 3, 0, 2, 0, 0};  // src/wfa2_utils.rs:183-189
+  return aligner_new(c, pen, out);
+}
+
+extern "C" int sfc_aligner_new_large_indel(sfc_ctx* c, int is_long_contig, sfc_aligner** out) {
+  // is_long_contig selects WFA2's MemoryMed vs MemoryHigh in the reference (src/wfa2_utils.rs:153-158); both are
+  // designed to return the same alignment and this implementation has a single (choice-byte) backtrace, so it is unused.
+  (void)is_long_contig;
+  const sfc_penalties pen = {1, -1, 3, 1, 2, 60, 0};  // src/wfa2_utils.rs:159-168
+  return aligner_new(c, pen, out);
+}
+
+extern "C" void sfc_aligner_free(sfc_aligner* a) { delete a; }
+
+extern "C" int sfc_aligner_set_text(sfc_aligner* a, const uint8_t* text, size_t len) {
+  if (!a) return SFC_ERR_INVALID;
+  if (!text || len == 0) return fail(a->ctx, SFC_ERR_INVALID, "set_text: empty text");  // assert!(!text.is_empty())
+  a->text.assign(text, text + len);
+  return SFC_OK;
+}
+
+extern "C" int sfc_aligner_align(sfc_aligner* a, const uint8_t* pattern, size_t len, int mode, double text_clip_frac,
+                                 double pattern_clip_frac, int32_t* score, int* has_alignment, int64_t* ref_offset, uint32_t* cigar,
+                                 size_t cigar_cap, size_t* n_cigar) {
+  if (!a || !score) return SFC_ERR_INVALID;
+  sfc_ctx* c = a->ctx;
+  if (a->text.empty()) return fail(c, SFC_ERR_INVALID, "align: text not set");
+  if (!pattern || len == 0) return fail(c, SFC_ERR_INVALID, "align: empty pattern");
+  std::vector<uint8_t> arena(a->text);
+  arena.insert(arena.end(), pattern, pattern + len);
+  sfc_pair pr;
+  memset(&pr, 0, sizeof(pr));
+  pr.text_off = 0; pr.text_len = (uint32_t)a->text.size();
+  pr.pattern_off = a->text.size(); pr.pattern_len = (uint32_t)len;
+  pr.flags = SFC_PAIR_REVERSE;
+  if (mode == 0) {  // src/wfa2_utils.rs:112-116
+    const int p_clip = (int)((double)len * 0.4), t_clip = (int)((double)a->text.size() * 0.4);
+    const int clip = std::min(p_clip, t_clip);
+    pr.pattern_begin_free = pr.pattern_end_free = pr.text_begin_free = pr.text_end_free = clip;
+  } else if (mode == 1) {  // src/wfa2_utils.rs:127-130
+    const int p_clip = (int)((double)len * pattern_clip_frac), t_clip = (int)((double)a->text.size() * text_clip_frac);
+    pr.pattern_begin_free = pr.pattern_end_free = p_clip;
+    pr.text_begin_free = pr.text_end_free = t_clip;
+  } else if (mode != 2) {
+    return fail(c, SFC_ERR_INVALID, "align: unknown mode %d", mode);
+  }
+  int32_t status = 0;
+  std::vector<uint32_t> ops(len + a->text.size() + 8);
+  uint64_t off[2] = {0, 0};
+  int rc = sfc_align_batch(c, &a->pen, arena.data(), arena.size(), &pr, 1, 1, score, &status, ops.data(), ops.size(), off);
+  if (rc) return rc;
+  if (status != 0) return fail(c, status, "align: pair status %d", status);
+  int hm = 0;
+  size_t nc = 0;
+  int64_t roff = 0;
+  rc = sfc_translate_rle(ops.data(), (size_t)off[1], &roff, cigar, cigar_cap, &nc, &hm);
+  if (rc) return fail(c, rc, "align: cigar translation failed (%d)", rc);
+  if (has_alignment) *has_alignment = hm;
+  if (ref_offset) *ref_offset = roff;
+  if (n_cigar) *n_cigar = nc;
+  return SFC_OK;
+}
+
+// ============================================================================ integer-ALU peak
+extern "C" int sfc_measure_int_peak(sfc_ctx* c, double* gops, double* mhz_est) {
+  if (!c || !gops) return SFC_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  const int blocks = c->sm_count * 8, threads = 256, iters = 4096;
+  DevBuf out;
+  int rc = ensure(c, out, (size_t)blocks * threads * 4);
+  if (rc) return rc;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(e0, c->stream));
+    int_peak_kernel<<<blocks, threads, 0, c->stream>>>((unsigned*)out.p, iters, 12345u + rep);
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double ops = (double)blocks * threads * (double)iters * 8.0 * 8.0 * 2.0;
+    best = std::max(best, ops / (ms * 1e-3) / 1e9);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  release(out);
+  *gops = best;
+  if (mhz_est) *mhz_est = best * 1e3 / ((double)c->sm_count * 64.0);  // assuming 64 INT32 lanes/SM/clk
+  return SFC_OK;
+}

@@ -1,0 +1,127 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) vs the CPU oracle, bit-exact.
+
+Run on the B200 box: python -m pytest tests -m gpu
+"""
+import numpy as np
+import pytest
+
+from helpers import compare_with_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _pens():
+    from sawfish_b200.batch import CONSENSUS_PENALTIES, LARGE_INDEL_PENALTIES
+    return CONSENSUS_PENALTIES, LARGE_INDEL_PENALTIES
+
+
+def test_native_library_loaded(ctx):
+    from sawfish_b200 import _lib
+    assert _lib.lib().sfc_device_count() >= 1
+
+
+def test_known_answer_consensus_aligner(ctx):
+    # reference src/wfa2_utils.rs:294-308
+    from sawfish_b200.simple_alignment import cigar_to_string
+    from sawfish_b200.wfa2_utils import PairwiseAligner
+    al = PairwiseAligner.new_consensus_aligner(ctx)
+    al.set_text(b"AACTGTATAA")
+    score, a = al.align(b"ACTTAT")
+    assert score == 4
+    assert a is not None and a.ref_offset == 1 and cigar_to_string(a.cigar) == "3=1D3="
+
+
+def test_pairwise_aligner_surface(ctx, oracle):
+    from sawfish_b200.simple_alignment import cigar_to_u32
+    from sawfish_b200.wfa2_utils import PairwiseAligner
+    rng = np.random.default_rng(7)
+    text = bytes(np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 400)])
+    pat = text[50:180] + b"ACGTTGCA" * 6 + text[180:350]
+    for ctor, pen in ((PairwiseAligner.new_consensus_aligner, oracle.CONSENSUS),
+                      (lambda c: PairwiseAligner.new_large_indel_aligner(False, c), oracle.LARGE_INDEL)):
+        al = ctor(ctx)
+        al.set_text(text)
+        assert al.text() == text[::-1]
+        for fn, kw in ((al.align, {}), (lambda p: al.align_clip_frac(p, 0.3, 0.1), dict(text_clip_frac=0.3, pattern_clip_frac=0.1)),
+                       (al.align_end_to_end, dict(end_to_end=True))):
+            score, a = fn(pat)
+            o_score, o_al, _ = oracle.sawfish_align(pen, text, pat, **kw)
+            assert score == o_score
+            assert (a is None) == (o_al is None)
+            if a is not None:
+                assert a.ref_offset == o_al[0] and cigar_to_u32(a.cigar) == o_al[1]
+    with pytest.raises(AssertionError):
+        PairwiseAligner.new_consensus_aligner(ctx).align(b"ACGT")  # text not set
+    with pytest.raises(AssertionError):
+        al.align(b"")
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("which", ["linear_score", "linear_cigar", "affine_cigar", "affine_score"])
+def test_random_small_pairs(ctx, oracle, seed, which):
+    from sawfish_b200 import synth
+    lin, aff = _pens()
+    arena, pairs = synth.random_pairs(1500, seed=seed * 101 + len(which), max_len=150)
+    pen = lin if which.startswith("linear") else aff
+    compare_with_oracle(oracle, ctx, pen, arena, pairs, want_cigar=which.endswith("cigar"), mode=oracle.MODE_LITERAL)
+
+
+def test_score_sv_shaped_batch(ctx, oracle):
+    # config 2b: 100-500 bp read flank vs ref/alt allele flanks, gap-linear, score only (K1)
+    from sawfish_b200 import synth
+    lin, _ = _pens()
+    arena, pairs, _ = synth.config2b_score_sv_flanks(3000)
+    compare_with_oracle(oracle, ctx, lin, arena, pairs, want_cigar=False)
+    st = ctx.stats()
+    assert st["n_score_kernel"] == len(pairs)
+    compare_with_oracle(oracle, ctx, lin, arena[:], pairs[:400], want_cigar=True)
+
+
+def test_refine_shaped_batch(ctx, oracle):
+    # config 3: contig vs reference window incl. 2-region alt-hap with the 100xN spacer, gap-affine-2p + CIGAR
+    from sawfish_b200 import synth
+    _, aff = _pens()
+    arena, pairs = synth.config3_refine_contigs(24, two_region_frac=0.3)
+    compare_with_oracle(oracle, ctx, aff, arena, pairs, want_cigar=True)
+
+
+def test_config2_reads_vs_haplotypes(ctx, oracle):
+    from sawfish_b200 import synth
+    lin, aff = _pens()
+    arena, pairs, _ = synth.config2_read_vs_haplotypes(8, len_lo=2000, len_hi=6000, sv_hi=1500)
+    compare_with_oracle(oracle, ctx, aff, arena, pairs, want_cigar=True)
+    compare_with_oracle(oracle, ctx, lin, arena, pairs, want_cigar=False)
+
+
+def test_edge_cases(ctx, oracle):
+    from sawfish_b200.batch import PAIR_DTYPE
+    lin, aff = _pens()
+    seqs = [b"A", b"C", b"N", b"NNNNNNNN", b"ACGT" * 10, b"A" * 40, b"AC" * 30, b"ACGTN" * 8, b"T" * 7 + b"G" + b"T" * 9]
+    arena = np.frombuffer(b"".join(seqs), np.uint8).copy()
+    offs = np.cumsum([0] + [len(s) for s in seqs])
+    rows = []
+    for i, p in enumerate(seqs):
+        for j, t in enumerate(seqs):
+            c = min(int(len(p) * 0.4), int(len(t) * 0.4))
+            rows.append((offs[i], offs[j], len(p), len(t), c, c, c, c, 1))
+            rows.append((offs[i], offs[j], len(p), len(t), 0, 0, 0, 0, 0))
+            rows.append((offs[i], offs[j], len(p), len(t), len(p), 0, 0, len(t), 0))
+    pairs = np.array(rows, dtype=PAIR_DTYPE)
+    for pen in (lin, aff):
+        for wc in (False, True):
+            compare_with_oracle(oracle, ctx, pen, arena, pairs, want_cigar=wc, mode=oracle.MODE_LITERAL)
+
+
+def test_invalid_inputs_fail_loudly(ctx):
+    from sawfish_b200.batch import PAIR_DTYPE, CONSENSUS_PENALTIES
+    from sawfish_b200 import SfcError
+    arena = np.frombuffer(b"ACGTACGTAC", np.uint8).copy()
+    ok = np.array([(0, 4, 4, 6, 1, 1, 1, 1, 1)], dtype=PAIR_DTYPE)
+    for bad in [(0, 4, 0, 6, 0, 0, 0, 0, 1), (0, 4, 4, 60, 0, 0, 0, 0, 1), (0, 4, 4, 6, 5, 0, 0, 0, 1)]:
+        with pytest.raises(SfcError):
+            ctx.align_batch(CONSENSUS_PENALTIES, arena, np.array([bad], dtype=PAIR_DTYPE), False)
+    bad_sym = np.frombuffer(b"ACGTAC*TAC", np.uint8).copy()
+    with pytest.raises(SfcError):
+        ctx.align_batch(CONSENSUS_PENALTIES, bad_sym, ok, False)
+    s, st, _, _ = ctx.align_batch(CONSENSUS_PENALTIES, arena, ok, False)
+    assert st[0] == 0
