@@ -1,0 +1,79 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports every symbol the header declares, and its
+host-only entry points (CIGAR translation / expansion) agree with the oracle.  No GPU compute here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sawfish_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "sawfish_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(sfc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTS)
+    L = C.CDLL(_lib.SO_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} not exported"
+    assert L.sfc_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from sawfish_b200.batch import PAIR_DTYPE
+    from sawfish_b200._lib import Penalties
+    assert PAIR_DTYPE.itemsize == 48 and C.sizeof(Penalties) == 28
+    assert [PAIR_DTYPE.fields[n][1] for n in PAIR_DTYPE.names] == [0, 8, 16, 20, 24, 28, 32, 36, 40]
+
+
+def test_no_gpu_means_loud_failure():
+    """Without a CUDA device there is no fallback: context creation fails with SFC_ERR_NO_DEVICE."""
+    from sawfish_b200 import _lib, SfcError
+    from sawfish_b200.batch import AlignContext
+    if _lib.lib().sfc_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(SfcError) as ei:
+        AlignContext(0)
+    assert ei.value.code == -2
+
+
+def test_product_package_does_not_import_oracle():
+    import sawfish_b200
+    pkg = os.path.dirname(sawfish_b200.__file__)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "wfa_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+def test_translate_cigar_matches_reference_vector_and_oracle(oracle):
+    from sawfish_b200.batch import translate_cigar, translate_rle, expand_ops
+    from sawfish_b200.simple_alignment import cigar_from_u32, cigar_to_string
+    from helpers import rle_of_bytes
+    roff, cig, hm = translate_cigar(b"DDDDMMMXXMMMMIIIMMMM"[::-1])   # reference src/wfa2_utils.rs:280-292
+    assert hm and roff == 0 and cigar_to_string(cigar_from_u32(cig)) == "4S3=2X4=3D4="
+    rng = np.random.default_rng(3)
+    for _ in range(500):
+        n = int(rng.integers(0, 40))
+        ops = bytes(rng.choice(np.frombuffer(b"MXIDMMMM", np.uint8), n))
+        want = oracle.translate_cigar(ops)
+        got = translate_cigar(ops)
+        assert got[0] == want[0] or not want[2]
+        assert list(got[1]) == want[1] and got[2] == want[2]
+        rle = rle_of_bytes(ops)
+        assert expand_ops(rle) == ops
+        got2 = translate_rle(rle)
+        assert got2[0] == got[0] and list(got2[1]) == list(got[1]) and got2[2] == got[2]
+
+
+def test_process_wfa2_cigar_string_mirror():
+    from sawfish_b200.wfa2_utils import process_wfa2_cigar_string
+    from sawfish_b200.simple_alignment import cigar_to_string
+    al = process_wfa2_cigar_string(b"DDDDMMMXXMMMMIIIMMMM"[::-1])
+    assert al is not None and al.ref_offset == 0 and cigar_to_string(al.cigar) == "4S3=2X4=3D4="
+    assert process_wfa2_cigar_string(b"DDII") is None
