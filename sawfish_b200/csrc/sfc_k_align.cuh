@@ -12,7 +12,7 @@
 //     the CTA's slab of device memory (HBM/L2) — a 20 kb x 20 kb pair needs ~22 MB of ring;
 //   * reads of source wavefronts are range-guarded from per-wavefront (lo,hi) metadata kept in shared
 //     memory, so rings are never initialised or cleared; trimming of every component to its first/last
-//     in-matrix diagonal is metadata only (one 11-way block reduction per score);
+//     in-matrix diagonal is metadata only (ten tiny warp scans from the row ends per score);
 //   * backtrace: instead of keeping every wavefront (WFA2 MemoryHigh) the kernel records ONE choice byte per
 //     (score, diagonal) at compute time using WFA2's tie-break priority
 //     (X > D2 > D1 > I2 > I1, extend >= open), walks the bytes back to score 0 (also yields k0 for the
@@ -21,9 +21,12 @@
 //     LITERAL mode).
 // Bound by integer ALU issue + L2/HBM traffic of the rings (~50 B per diagonal per score); no tensor cores.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "sfc_device.cuh"
 
 namespace sfc {
+namespace cg = cooperative_groups;
 
 enum { K2_SEL_X = 0, K2_SEL_I1 = 1, K2_SEL_I2 = 2, K2_SEL_D1 = 3, K2_SEL_D2 = 4 };
 constexpr uint32_t K2_BIT_I1E = 0x08, K2_BIT_I2E = 0x10, K2_BIT_D1E = 0x20, K2_BIT_D2E = 0x40;
@@ -75,22 +78,28 @@ __device__ __forceinline__ long long k2_gap_cost(const K2Params& P, int L) {
 template <bool AFF>
 __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
   extern __shared__ __align__(16) unsigned char k2_smem[];
+  // A pair is aligned by one CTA, or by a thread-block cluster of C CTAs (C SMs) for long haplotypes: the
+  // CTAs of a cluster stride the diagonals of each wavefront together, share the rings / choice bytes in
+  // global memory (cluster-scope release/acquire at each barrier) and exchange the few words of per-score
+  // metadata through distributed shared memory.
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, NW = NT >> 5;
-  constexpr int NRED = AFF ? 11 : 3;
+  auto csync = [&]() { if (C > 1) cluster.sync(); else __syncthreads(); };
   const int nslots = AFF ? P.nM + 2 * P.nG1 + 2 * P.nG2 : P.nM;
   uint2* win = reinterpret_cast<uint2*>(k2_smem);
   int* meta = reinterpret_cast<int*>(win + P.win_cap);  // [nslots][2]
-  int* part = meta + 2 * nslots;                        // [2][32][NRED]
-  int* misc = part + 2 * 32 * NRED;                     // [0] pair idx, [1..] backtrace broadcast
-  unsigned char* slab = P.slabs + (size_t)blockIdx.x * P.slab_bytes;
+  int* misc = meta + 2 * nslots;                        // [0] pair idx, [1] terminating diagonal
+  unsigned char* slab = P.slabs + (size_t)(blockIdx.x / C) * P.slab_bytes;
+  int* misc0 = C > 1 ? cluster.map_shared_rank(misc, 0) : misc;  // rank 0's copy: work index + terminating diagonal
   unsigned long long cells_acc = 0;
 
   for (;;) {
-    __syncthreads();
-    if (tid == 0) misc[0] = (int)atomicAdd(P.counter, 1u);
-    __syncthreads();
-    const uint32_t wi = (uint32_t)misc[0];
-    if (wi >= P.n) break;
+    csync();
+    if (crank == 0 && tid == 0) { misc[0] = (int)atomicAdd(P.counter, 1u); misc[1] = INT_MAX; }
+    csync();
+    const uint32_t wi = (uint32_t)misc0[0];
+    if (wi >= P.n) { csync(); break; }  // no CTA may exit while a peer can still read its shared memory
     const uint32_t pi = P.order[wi];
     const DevPair pr = P.pairs[pi];
     const int plen = pr.plen, tlen = pr.tlen;
@@ -112,7 +121,7 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
     if (nwp + nwt > P.win_cap) res_status = -5;
     else if (fixed + 1024 > P.slab_bytes) res_status = -6;
     if (res_status != 0) {
-      if (tid == 0) { P.scores[pi] = 0; P.status[pi] = res_status; P.out_len[pi] = 0; P.out_off[pi] = 0; }
+      if (crank == 0 && tid == 0) { P.scores[pi] = 0; P.status[pi] = res_status; P.out_len[pi] = 0; P.out_off[pi] = 0; }
       continue;
     }
     int32_t* rings = reinterpret_cast<int32_t*>(slab);
@@ -131,11 +140,8 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
     }
     __syncthreads();
 
-    // slot bases per component
+    // slot bases per component (row index == slot index); all row offsets are 32-bit element offsets into rings
     const int sbM = 0, sbI1 = P.nM, sbD1 = P.nM + P.nG1, sbI2 = P.nM + 2 * P.nG1, sbD2 = P.nM + 2 * P.nG1 + P.nG2;
-    K2Range last[5];  // metadata of score s-1 (register copy, so one barrier per score suffices)
-#pragma unroll
-    for (int c = 0; c < 5; ++c) { last[c].lo = 1; last[c].hi = -1; }
     auto slot_of = [&](int c, int sc) -> int {
       switch (c) {
         case K2_C_M: return sbM + sc % P.nM;
@@ -145,8 +151,16 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
         default: return sbD2 + sc % P.nG2;
       }
     };
+    auto get = [&](int c, int sc) -> K2Range {
+      K2Range r; r.lo = 1; r.hi = -1;
+      if (sc < 0) return r;
+      const int sl = slot_of(c, sc);
+      r.lo = meta[2 * sl]; r.hi = meta[2 * sl + 1];
+      return r;
+    };
+    int* term_slot = misc0 + 1;  // cluster-wide min of terminating diagonals (reset at pair fetch)
 
-    int s = 0, par = 0, end_k = 0;
+    int s = 0, end_k = 0;
     bool done = false;
     for (;; ++s) {
       if (s > S_cap) { res_status = -7; break; }
@@ -154,28 +168,18 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
       const int s_mx = s - P.x;
       const int s_o1 = AFF ? s - P.o1 - P.e1 : s - P.e1;
       const int s_o2 = s - P.o2 - P.e2, s_e1 = s - P.e1, s_e2 = s - P.e2;
-      auto get = [&](int c, int sc) -> K2Range {
-        K2Range r; r.lo = 1; r.hi = -1;
-        if (sc < 0 || s == 0) return r;
-        if (sc == s - 1) return last[c];
-        const int sl = slot_of(c, sc);
-        r.lo = meta[2 * sl]; r.hi = meta[2 * sl + 1];
-        return r;
-      };
-      const K2Range MX = get(K2_C_M, s_mx), MO1 = get(K2_C_M, s_o1);
-      K2Range MO2, I1E, D1E, I2E, D2E;
-      MO2.lo = I1E.lo = D1E.lo = I2E.lo = D2E.lo = 1;
-      MO2.hi = I1E.hi = D1E.hi = I2E.hi = D2E.hi = -1;
-      if (AFF) {
-        MO2 = get(K2_C_M, s_o2); I1E = get(K2_C_I1, s_e1); D1E = get(K2_C_D1, s_e1);
-        I2E = get(K2_C_I2, s_e2); D2E = get(K2_C_D2, s_e2);
-      }
+      K2Range MX, MO1, MO2, I1E, D1E, I2E, D2E;
+      MX.lo = MO1.lo = MO2.lo = I1E.lo = D1E.lo = I2E.lo = D2E.lo = 1;
+      MX.hi = MO1.hi = MO2.hi = I1E.hi = D1E.hi = I2E.hi = D2E.hi = -1;
       int lo = INT_MAX, hi = INT_MIN;
       if (s == 0) { lo = -pr.pbf; hi = pr.tbf; }
       else {
+        MX = get(K2_C_M, s_mx); MO1 = get(K2_C_M, s_o1);
         if (MX.any()) { lo = min(lo, MX.lo); hi = max(hi, MX.hi); }
         if (MO1.any()) { lo = min(lo, MO1.lo - 1); hi = max(hi, MO1.hi + 1); }
         if (AFF) {
+          MO2 = get(K2_C_M, s_o2); I1E = get(K2_C_I1, s_e1); D1E = get(K2_C_D1, s_e1);
+          I2E = get(K2_C_I2, s_e2); D2E = get(K2_C_D2, s_e2);
           if (MO2.any()) { lo = min(lo, MO2.lo - 1); hi = max(hi, MO2.hi + 1); }
           if (I1E.any()) { lo = min(lo, I1E.lo + 1); hi = max(hi, I1E.hi + 1); }
           if (D1E.any()) { lo = min(lo, D1E.lo - 1); hi = max(hi, D1E.hi - 1); }
@@ -184,14 +188,9 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
         }
       }
       if (lo > hi) {  // wavefront s does not exist
-        if (tid == 0) {
-          meta[2 * slot_of(K2_C_M, s)] = 1; meta[2 * slot_of(K2_C_M, s) + 1] = -1;
-          if (AFF) {
-            for (int c = 1; c < 5; ++c) { meta[2 * slot_of(c, s)] = 1; meta[2 * slot_of(c, s) + 1] = -1; }
-          }
+        if (tid == 0) {  // every CTA marks its own copy
+          for (int c = 0; c < (AFF ? 5 : 1); ++c) { meta[2 * slot_of(c, s)] = 1; meta[2 * slot_of(c, s) + 1] = -1; }
         }
-#pragma unroll
-        for (int c = 0; c < 5; ++c) { last[c].lo = 1; last[c].hi = -1; }
         __syncthreads();
         continue;
       }
@@ -214,27 +213,19 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
         }
         if (!ok || s == 0) { ilo = 1; ihi = 0; }
       }
-      const int32_t* rMX = rings + (size_t)slot_of(K2_C_M, max(s_mx, 0)) * Wp + kbase;
-      const int32_t* rMO1 = rings + (size_t)slot_of(K2_C_M, max(s_o1, 0)) * Wp + kbase;
-      const int32_t* rMO2 = rings + (size_t)slot_of(K2_C_M, max(s_o2, 0)) * Wp + kbase;
-      const int32_t* rI1E = rings + (size_t)slot_of(K2_C_I1, max(s_e1, 0)) * Wp + kbase;
-      const int32_t* rD1E = rings + (size_t)slot_of(K2_C_D1, max(s_e1, 0)) * Wp + kbase;
-      const int32_t* rI2E = rings + (size_t)slot_of(K2_C_I2, max(s_e2, 0)) * Wp + kbase;
-      const int32_t* rD2E = rings + (size_t)slot_of(K2_C_D2, max(s_e2, 0)) * Wp + kbase;
-      int32_t* oM = rings + (size_t)slot_of(K2_C_M, s) * Wp + kbase;
-      int32_t* oI1 = rings + (size_t)slot_of(K2_C_I1, s) * Wp + kbase;
-      int32_t* oD1 = rings + (size_t)slot_of(K2_C_D1, s) * Wp + kbase;
-      int32_t* oI2 = rings + (size_t)slot_of(K2_C_I2, s) * Wp + kbase;
-      int32_t* oD2 = rings + (size_t)slot_of(K2_C_D2, s) * Wp + kbase;
-      unsigned char* btrow = bt + bt_used;
+      const int32_t* __restrict__ R = rings;
+      const int qMX = slot_of(K2_C_M, max(s_mx, 0)) * Wp + kbase, qMO1 = slot_of(K2_C_M, max(s_o1, 0)) * Wp + kbase;
+      const int qMO2 = slot_of(K2_C_M, max(s_o2, 0)) * Wp + kbase;
+      const int qI1E = slot_of(K2_C_I1, max(s_e1, 0)) * Wp + kbase, qD1E = slot_of(K2_C_D1, max(s_e1, 0)) * Wp + kbase;
+      const int qI2E = slot_of(K2_C_I2, max(s_e2, 0)) * Wp + kbase, qD2E = slot_of(K2_C_D2, max(s_e2, 0)) * Wp + kbase;
+      const int wM = slot_of(K2_C_M, s) * Wp + kbase, wI1 = slot_of(K2_C_I1, s) * Wp + kbase, wD1 = slot_of(K2_C_D1, s) * Wp + kbase;
+      const int wI2 = slot_of(K2_C_I2, s) * Wp + kbase, wD2 = slot_of(K2_C_D2, s) * Wp + kbase;
+      unsigned char* btrow = bt + bt_used - lo;  // indexed by k
       const int cMX = MX.cnt(), cMO1 = MO1.cnt(), cMO2 = MO2.cnt(), cI1E = I1E.cnt(), cD1E = D1E.cnt(),
                 cI2E = I2E.cnt(), cD2E = D2E.cnt();
+      int term_k = INT_MAX;
 
-      int red[NRED];  // all as minima: [0] term_k, then (lo, -hi) per component
-#pragma unroll
-      for (int j = 0; j < NRED; ++j) red[j] = INT_MAX;
-
-      for (int kb = lo + warp * 32; kb <= hi; kb += NT) {
+      for (int kb = lo + (crank * NW + warp) * 32; kb <= hi; kb += C * NT) {
         const int k = kb + lane;
         const bool act = k <= hi;
         int32_t best = WNULL, ins1 = WNULL, ins2 = WNULL, del1 = WNULL, del2 = WNULL;
@@ -244,23 +235,23 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
         } else {
           int32_t mx, i1o, d1o, i1e = WNULL, d1e = WNULL, i2o = WNULL, d2o = WNULL, i2e = WNULL, d2e = WNULL;
           if (kb >= ilo && kb + 31 <= ihi) {
-            mx = rMX[k]; i1o = rMO1[k - 1]; d1o = rMO1[k + 1];
+            mx = R[qMX + k]; i1o = R[qMO1 + k - 1]; d1o = R[qMO1 + k + 1];
             if (AFF) {
-              i1e = rI1E[k - 1]; d1e = rD1E[k + 1];
-              if (has2) { i2o = rMO2[k - 1]; d2o = rMO2[k + 1]; i2e = rI2E[k - 1]; d2e = rD2E[k + 1]; }
+              i1e = R[qI1E + k - 1]; d1e = R[qD1E + k + 1];
+              if (has2) { i2o = R[qMO2 + k - 1]; d2o = R[qMO2 + k + 1]; i2e = R[qI2E + k - 1]; d2e = R[qD2E + k + 1]; }
             }
           } else {
-            mx = k2_guard(rMX, k, MX.lo, cMX);
-            i1o = k2_guard(rMO1, k - 1, MO1.lo, cMO1);
-            d1o = k2_guard(rMO1, k + 1, MO1.lo, cMO1);
+            mx = k2_guard(R + qMX, k, MX.lo, cMX);
+            i1o = k2_guard(R + qMO1, k - 1, MO1.lo, cMO1);
+            d1o = k2_guard(R + qMO1, k + 1, MO1.lo, cMO1);
             if (AFF) {
-              i1e = k2_guard(rI1E, k - 1, I1E.lo, cI1E);
-              d1e = k2_guard(rD1E, k + 1, D1E.lo, cD1E);
+              i1e = k2_guard(R + qI1E, k - 1, I1E.lo, cI1E);
+              d1e = k2_guard(R + qD1E, k + 1, D1E.lo, cD1E);
               if (has2) {
-                i2o = k2_guard(rMO2, k - 1, MO2.lo, cMO2);
-                d2o = k2_guard(rMO2, k + 1, MO2.lo, cMO2);
-                i2e = k2_guard(rI2E, k - 1, I2E.lo, cI2E);
-                d2e = k2_guard(rD2E, k + 1, D2E.lo, cD2E);
+                i2o = k2_guard(R + qMO2, k - 1, MO2.lo, cMO2);
+                d2o = k2_guard(R + qMO2, k + 1, MO2.lo, cMO2);
+                i2e = k2_guard(R + qI2E, k - 1, I2E.lo, cI2E);
+                d2e = k2_guard(R + qD2E, k + 1, D2E.lo, cD2E);
               }
             }
           }
@@ -282,7 +273,6 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
             if (del >= best) { best = del; ch = K2_SEL_D1; }
             if (mis >= best) { best = mis; ch = K2_SEL_X; }
           }
-          if (!act) { best = WNULL; ins1 = ins2 = del1 = del2 = WNULL; }
         }
         if (!k2_in_matrix(best, k, plen, tlen)) best = WNULL;
         // ---- extend M along matches ----
@@ -309,63 +299,74 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
         }
         if (best >= 0) {
           const int v = off - k;
-          if ((off >= tlen && plen - v <= pr.pef) || (v >= plen && tlen - off <= pr.tef)) red[0] = min(red[0], k);
-          red[1] = min(red[1], k); red[2] = min(red[2], -k);
+          if ((off >= tlen && plen - v <= pr.pef) || (v >= plen && tlen - off <= pr.tef)) term_k = min(term_k, k);
         }
         if (act) {
-          oM[k] = best >= 0 ? off : WNULL;
-          if (s > 0) btrow[k - lo] = (unsigned char)ch;
-          if (AFF && s > 0) {
-            oI1[k] = ins1; oD1[k] = del1;
-            if (k2_in_matrix(ins1, k, plen, tlen)) { red[3] = min(red[3], k); red[4] = min(red[4], -k); }
-            if (k2_in_matrix(del1, k, plen, tlen)) { red[5] = min(red[5], k); red[6] = min(red[6], -k); }
-            if (has2) {
-              oI2[k] = ins2; oD2[k] = del2;
-              if (k2_in_matrix(ins2, k, plen, tlen)) { red[7] = min(red[7], k); red[8] = min(red[8], -k); }
-              if (k2_in_matrix(del2, k, plen, tlen)) { red[9] = min(red[9], k); red[10] = min(red[10], -k); }
+          rings[wM + k] = off;  // off == WNULL when the cell is null
+          if (s > 0) {
+            btrow[k] = (unsigned char)ch;
+            if (AFF) {
+              rings[wI1 + k] = ins1; rings[wD1 + k] = del1;
+              if (has2) { rings[wI2 + k] = ins2; rings[wD2 + k] = del2; }
             }
           }
         }
       }
-      // ---- block reduction: termination diagonal + trimmed ranges ----
-      int* pp = part + par * 32 * NRED;
-#pragma unroll
-      for (int j = 0; j < NRED; ++j) {
-        const int v = warp_min(red[j]);
-        if (lane == 0) pp[warp * NRED + j] = v;
+      // ---- barrier 1: rows of score s complete; did any diagonal terminate? ----
+      term_k = warp_min(term_k);
+      if (term_k != INT_MAX && lane == 0) atomicMin(term_slot, term_k);
+      csync();
+      const int tk = *term_slot;
+      if (tk != INT_MAX) {
+        end_k = tk; done = true;
+        if (crank == 0 && tid == 0) { rowoff[s] = bt_used; rowlo[s] = lo; cells_acc += (unsigned long long)width; }
+        break;
       }
-      __syncthreads();
-#pragma unroll
-      for (int j = 0; j < NRED; ++j) red[j] = warp_min(lane < NW ? pp[lane * NRED + j] : INT_MAX);
-      par ^= 1;
-      K2Range now[5];
-#pragma unroll
-      for (int c = 0; c < 5; ++c) { now[c].lo = 1; now[c].hi = -1; }
-#pragma unroll
-      for (int c = 0; c < (AFF ? 5 : 1); ++c) {
-        const int l = red[1 + 2 * c], h = red[2 + 2 * c];
-        if (l != INT_MAX) { now[c].lo = l; now[c].hi = -h; }
-      }
-      if (tid == 0) {
-#pragma unroll
-        for (int c = 0; c < (AFF ? 5 : 1); ++c) {
+      // ---- trim every component to its first / last in-matrix diagonal (metadata only) ----
+      {
+        const int ncomp = AFF ? 5 : 1;
+        for (int task = crank * NW + warp; task < 2 * ncomp; task += C * NW) {
+          const int c = task >> 1, side = task & 1;
           const int sl = slot_of(c, s);
-          meta[2 * sl] = now[c].lo; meta[2 * sl + 1] = now[c].hi;
+          int found = side ? -1 : 1;  // empty encoding: lo = 1, hi = -1
+          if (c == K2_C_M || s > 0) {
+            if ((c == K2_C_I2 || c == K2_C_D2) && !has2) {
+              // piece-2 wavefronts do not exist yet
+            } else {
+              const int q = (c == K2_C_M ? wM : c == K2_C_I1 ? wI1 : c == K2_C_D1 ? wD1 : c == K2_C_I2 ? wI2 : wD2);
+              bool got = false;
+              if (!side) {
+                for (int base = lo; base <= hi && !got; base += 32) {
+                  const int k = base + lane;
+                  const bool inm = (k <= hi) && k2_in_matrix(rings[q + k], k, plen, tlen);
+                  const unsigned b = __ballot_sync(FULL, inm);
+                  if (b) { found = base + __ffs((int)b) - 1; got = true; }
+                }
+              } else {
+                for (int base = hi; base >= lo && !got; base -= 32) {
+                  const int k = base - lane;
+                  const bool inm = (k >= lo) && k2_in_matrix(rings[q + k], k, plen, tlen);
+                  const unsigned b = __ballot_sync(FULL, inm);
+                  if (b) { found = base - (__ffs((int)b) - 1); got = true; }
+                }
+              }
+            }
+          }
+          if (lane == 0) {
+            if (C > 1) { for (int r = 0; r < C; ++r) cluster.map_shared_rank(meta, r)[2 * sl + side] = found; }
+            else meta[2 * sl + side] = found;
+          }
         }
-        rowoff[s] = bt_used;
-        rowlo[s] = lo;
-        cells_acc += (unsigned long long)width;
+        if (crank == 0 && tid == 0) { rowoff[s] = bt_used; rowlo[s] = lo; cells_acc += (unsigned long long)width; }
       }
-#pragma unroll
-      for (int c = 0; c < 5; ++c) last[c] = now[c];
       if (s > 0) bt_used += (unsigned long long)width;
-      if (red[0] != INT_MAX) { end_k = red[0]; done = true; break; }
+      csync();  // barrier 2: metadata of score s visible
     }
 
     // ---- backtrace (warp 0): choice walk to score 0, then forward replay ----
     if (done) {
-      __syncthreads();  // rowoff/rowlo/bt/oM of the last step visible to warp 0
-      if (warp == 0) {
+      csync();  // rowoff/rowlo/bt/oM of the last step visible to warp 0 of rank 0
+      if (crank == 0 && warp == 0) {
         const int32_t* oM = rings + (size_t)slot_of(K2_C_M, s) * Wp + kbase;
         const int end_off = oM[end_k];
         int k0 = 0, nb = 0, bad = 0;
@@ -479,11 +480,11 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
         if (bad) res_status = -9;
         if (lane == 0) { P.scores[pi] = res_score; P.status[pi] = res_status; P.out_off[pi] = o_off; P.out_len[pi] = o_len; }
       }
-    } else if (tid == 0) {
+    } else if (crank == 0 && tid == 0) {
       P.scores[pi] = 0; P.status[pi] = res_status; P.out_off[pi] = 0; P.out_len[pi] = 0;
     }
   }
-  if (tid == 0 && cells_acc) atomicAdd(P.cells, cells_acc);
+  if (crank == 0 && tid == 0 && cells_acc) atomicAdd(P.cells, cells_acc);
 }
 
 }  // namespace sfc

@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -42,6 +43,8 @@ struct sfc_ctx {
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
+  cudaStream_t job_stream[6] = {};  // concurrent K2 jobs (one per size class / cluster size)
+  cudaEvent_t job_ev[7] = {};
   std::string err;
   size_t ws_limit = 0;
   // device buffers
@@ -209,6 +212,12 @@ extern "C" int sfc_create(int device_ordinal, sfc_ctx** out) {
   for (auto& e : c->ev) {
     if (cudaEventCreate(&e) != cudaSuccess) { sfc_destroy(c); return SFC_ERR_CUDA; }
   }
+  for (auto& st : c->job_stream) {
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { sfc_destroy(c); return SFC_ERR_CUDA; }
+  }
+  for (auto& e : c->job_ev) {
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { sfc_destroy(c); return SFC_ERR_CUDA; }
+  }
   uint8_t lut[256];
   init_lut_host(lut);
   if (cudaMemcpyToSymbol(c_nib_lut, lut, 256) != cudaSuccess) { sfc_destroy(c); return SFC_ERR_CUDA; }
@@ -224,6 +233,8 @@ extern "C" void sfc_destroy(sfc_ctx* c) {
                     &c->d_misc, &c->d_pool, &c->d_outoff, &c->d_outlen, &c->d_ws})
     release(*b);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : c->job_ev) if (e) cudaEventDestroy(e);
+  for (auto& st : c->job_stream) if (st) cudaStreamDestroy(st);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -411,131 +422,216 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     c->stats.launches++;
   }
 
-  // ---- K2 launches (with workspace escalation) ----
+  // ---- K2 launches: jobs by (size class, cluster size), heaviest first, with workspace escalation ----
   c->pool_used = 0;
   if (k2s_begin < n) {
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     size_t avail = (size_t)((double)(free_b + c->d_ws.cap + c->d_pool.cap) * 0.85);
     if (c->ws_limit && avail > c->ws_limit) avail = c->ws_limit;
-    // output pool
     size_t pool_cap = want_cigar ? std::max<size_t>((n - k2s_begin) * 64, (size_t)1 << 20) : 16;
     if ((rc = ensure(c, c->d_pool, pool_cap * 4))) return rc;
     pool_cap = c->d_pool.cap / 4;
     const int nM = (a.metric == 1 ? std::max(a.x, std::max(a.o1 + a.e1, a.o2 + a.e2)) : lookL) + 1;
     const int nG1 = a.e1 + 1, nG2 = a.e2 + 1;
     const int nslots = a.metric == 1 ? nM + 2 * nG1 + 2 * nG2 : nM;
-    const int nred = a.metric == 1 ? 11 : 3;
+    const void* kfn = a.metric == 1 ? (const void*)k2_align<true> : (const void*)k2_align<false>;
 
-    struct Job { size_t begin, count; int threads; };
-    Job jobs[2] = {{k2s_begin, k2l_begin - k2s_begin, 128}, {k2l_begin, n - k2l_begin, 512}};
-    std::vector<uint32_t> retry;
-    for (int jj = 0; jj < 2; ++jj) {
-      Job job = jobs[jj];
-      if (!job.count) continue;
-      const uint32_t* order_host = c->h_order.data() + job.begin;
-      const uint32_t* order_dev = (const uint32_t*)c->d_order.p + job.begin;
-      size_t count = job.count;
-      int divisor = 1;
-      for (int pass = 0; pass < 12; ++pass) {
-        // fixed workspace need and shared-memory need of the heaviest pair in this pass
-        size_t max_fixed = 0, max_win = 0, max_W = 0;
-        for (size_t q = 0; q < count; ++q) {
-          const DevPair& d = c->h_pairs[order_host[q]];
-          const size_t Wp = (size_t)d.plen + d.tlen + 5;
-          long long scap = gap_cost(a, d.plen) + gap_cost(a, d.tlen) + 1;
-          scap = std::min<long long>(scap, INT_MAX / 4);
-          const size_t fixed = (size_t)nslots * Wp * 4 + ((size_t)scap + 1) * 12 + 2 * (((size_t)d.plen + d.tlen + 8) * 4) + 256;
-          max_fixed = std::max(max_fixed, fixed);
-          max_win = std::max(max_win, (size_t)(d.plen >> 3) + (d.tlen >> 3) + 2);
-          max_W = std::max(max_W, Wp);
-        }
-        const size_t smem = max_win * 8 + (size_t)nslots * 8 + (size_t)2 * 32 * nred * 4 + 64;
-        if (smem > c->smem_optin) {
-          // sequences do not fit shared memory: report per-pair status from the kernel (win_cap check) with a capped size
-        }
-        const size_t smem_use = std::min(smem, c->smem_optin);
-        const int win_cap = (int)((smem_use - (size_t)nslots * 8 - (size_t)2 * 32 * nred * 4 - 64) / 8);
-        int occ = 1;
-        if (a.metric == 1) {
-          CU(cudaFuncSetAttribute(k2_align<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_use));
-          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_align<true>, job.threads, smem_use));
-        } else {
-          CU(cudaFuncSetAttribute(k2_align<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_use));
-          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_align<false>, job.threads, smem_use));
-        }
-        occ = std::max(1, occ);
-        size_t n_cta = std::min<size_t>(count, (size_t)c->sm_count * occ);
-        n_cta = std::max<size_t>(1, n_cta / divisor);
-        // choice-byte budget: a few thousand score rows of the widest pair, escalated on retry
-        size_t bt_want = std::min<size_t>(std::max<size_t>((size_t)2048 * max_W * divisor, (size_t)4 << 20), (size_t)8 << 30);
-        size_t slab = max_fixed + bt_want;
-        while (n_cta > 1 && slab * n_cta > avail) n_cta = (n_cta + 1) / 2;
-        if (slab * n_cta > avail) slab = avail;
-        if (slab < max_fixed + 4096) return fail(c, SFC_ERR_OOM, "device workspace too small: need %zu B for one pair", max_fixed);
-        slab &= ~(size_t)255;
-        if ((rc = ensure(c, c->d_ws, slab * n_cta))) return rc;
-        K2Params P;
-        P.pairs = (const DevPair*)c->d_pairs.p;
-        P.order = order_dev;
-        P.n = (uint32_t)count;
-        P.counter = misc + 8;
-        P.nib = (const uint32_t*)c->d_nib.p;
-        P.scores = (int32_t*)c->d_scores.p;
-        P.status = (int32_t*)c->d_status.p;
-        P.metric = a.metric; P.x = a.x; P.o1 = a.o1; P.e1 = a.e1; P.o2 = a.o2; P.e2 = a.e2; P.match = a.match;
-        P.nM = nM; P.nG1 = nG1; P.nG2 = nG2;
-        P.slabs = (unsigned char*)c->d_ws.p;
-        P.slab_bytes = slab;
-        P.want_cigar = c->want_cigar;
-        P.pool = (uint32_t*)c->d_pool.p;
-        P.pool_cap = pool_cap;
-        P.pool_used = (unsigned long long*)(misc + 4);
-        P.out_off = (unsigned long long*)c->d_outoff.p;
-        P.out_len = (uint32_t*)c->d_outlen.p;
-        P.cells = (unsigned long long*)(misc + 2);
-        P.win_cap = win_cap;
-        P.max_score = INT_MAX / 4;
-        CU(cudaMemsetAsync(misc + 8, 0, 4, c->stream));
-        if (a.metric == 1) k2_align<true><<<(int)n_cta, job.threads, smem_use, c->stream>>>(P);
-        else k2_align<false><<<(int)n_cta, job.threads, smem_use, c->stream>>>(P);
-        CU(cudaGetLastError());
-        c->stats.launches++;
-        // ---- look for pairs that ran out of slab (-6) or of pool (-4) ----
-        c->h_status.resize(n);
-        CU(cudaMemcpyAsync(c->h_status.data(), c->d_status.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        retry.clear();
-        bool pool_short = false;
-        for (size_t q = 0; q < count; ++q) {
-          const int st = c->h_status[order_host[q]];
-          if (st == SFC_STATUS_OOM) retry.push_back(order_host[q]);
-          else if (st == -4) { retry.push_back(order_host[q]); pool_short = true; }
-        }
-        if (retry.empty()) break;
-        if (n_cta == 1 && slab >= avail - 4096 && !pool_short) break;  // nothing left to escalate: statuses stay -6
-        c->stats.retries++;
-        if (pool_short) {
-          // keep what is already in the pool, grow it for the rest
-          unsigned long long used = 0;
-          CU(cudaMemcpy(&used, misc + 4, 8, cudaMemcpyDeviceToHost));
-          DevBuf bigger;
-          size_t new_cap = std::max<size_t>(pool_cap * 4, (size_t)used + ((size_t)1 << 22));
-          if ((rc = ensure(c, bigger, new_cap * 4))) return rc;
-          CU(cudaMemcpy(bigger.p, c->d_pool.p, std::min<size_t>((size_t)used, pool_cap) * 4, cudaMemcpyDeviceToDevice));
-          // pool_used may have overshot the old capacity: reset it to the last valid fill level
-          // (entries are only written when they fit, so every recorded out_off/out_len is below pool_cap)
-          release(c->d_pool);
-          c->d_pool = bigger;
-          pool_cap = c->d_pool.cap / 4;
-          // the overshoot (failed reservations) leaves holes but never overlaps valid data
-        }
-        divisor *= 4;
-        // retry list becomes the new order (reuse the tail of d_order belonging to this job)
-        CU(cudaMemcpyAsync((uint32_t*)c->d_order.p + job.begin, retry.data(), retry.size() * 4, cudaMemcpyHostToDevice, c->stream));
-        std::copy(retry.begin(), retry.end(), c->h_order.begin() + job.begin);
-        count = retry.size();
+    struct Job { std::vector<uint32_t> list; int threads; int C; };
+    std::vector<Job> jobs;
+    // small pairs: one 128-thread CTA each
+    if (k2l_begin > k2s_begin) jobs.push_back(Job{std::vector<uint32_t>(c->h_order.begin() + k2s_begin, c->h_order.begin() + k2l_begin), 128, 1});
+    // large pairs: 512-thread CTAs; a pair whose estimated work exceeds the balanced per-SM share is spread over a
+    // thread-block cluster of 2/4/8 CTAs so that the heaviest alignment does not set the batch time
+    if (n > k2l_begin) {
+      const size_t nl = n - k2l_begin;
+      std::vector<double> est(nl);
+      double total = 0;
+      for (size_t q = 0; q < nl; ++q) {
+        const DevPair& d = c->h_pairs[c->h_order[k2l_begin + q]];
+        const double dl = std::abs((double)d.plen - (double)d.tlen);
+        const double es = (double)gap_cost(a, (long long)dl) + 0.012 * 0.5 * ((double)d.plen + d.tlen) + 8.0;
+        est[q] = es * ((double)d.pbf + d.tbf + 1.0 + 0.4 * es);
+        total += est[q];
       }
+      int force_c = 0;
+      if (const char* e = getenv("SFC_K2_CLUSTER")) force_c = atoi(e);
+      const double share = std::max(total / (double)c->sm_count, 2e6);
+      std::vector<uint32_t> byc[4];
+      std::vector<std::pair<double, uint32_t>> tmp[4];
+      for (size_t q = 0; q < nl; ++q) {
+        int ci = 0;
+        double r = est[q] / share;
+        while (ci < 3 && r > 1.0) { r *= 0.5; ++ci; }
+        if (force_c == 1) ci = 0; else if (force_c == 2) ci = 1; else if (force_c == 4) ci = 2; else if (force_c == 8) ci = 3;
+        tmp[ci].push_back({est[q], c->h_order[k2l_begin + q]});
+      }
+      for (int ci = 3; ci >= 0; --ci) {
+        if (tmp[ci].empty()) continue;
+        std::stable_sort(tmp[ci].begin(), tmp[ci].end(), [](const std::pair<double, uint32_t>& x, const std::pair<double, uint32_t>& y) { return x.first > y.first; });
+        Job j; j.threads = 512; j.C = 1 << ci;
+        for (auto& t : tmp[ci]) j.list.push_back(t.second);
+        jobs.push_back(std::move(j));
+      }
+    }
+
+    // size one job's launch: returns grid (in clusters), slab bytes, shared bytes, win_cap
+    struct Plan { size_t n_cl, slab, smem, max_fixed; int win_cap; };
+    size_t smem_attr = 0;
+    auto plan_job = [&](const std::vector<uint32_t>& list, int threads, int C, size_t budget, int divisor, Plan* pl) -> int {
+      size_t max_fixed = 0, max_win = 0, max_W = 0;
+      for (uint32_t pi : list) {
+        const DevPair& d = c->h_pairs[pi];
+        const size_t Wp = (size_t)d.plen + d.tlen + 5;
+        long long scap = gap_cost(a, d.plen) + gap_cost(a, d.tlen) + 1;
+        scap = std::min<long long>(scap, INT_MAX / 4);
+        const size_t fixed = (size_t)nslots * Wp * 4 + ((size_t)scap + 1) * 12 + 2 * (((size_t)d.plen + d.tlen + 8) * 4) + 256;
+        max_fixed = std::max(max_fixed, fixed);
+        max_win = std::max(max_win, (size_t)(d.plen >> 3) + (d.tlen >> 3) + 2);
+        max_W = std::max(max_W, Wp);
+      }
+      const size_t smem = std::min(max_win * 8 + (size_t)nslots * 8 + 64, c->smem_optin);
+      pl->smem = smem;
+      pl->win_cap = (int)((smem - (size_t)nslots * 8 - 64) / 8);
+      pl->max_fixed = max_fixed;
+      smem_attr = std::max(smem_attr, smem);  // the attribute must cover every job launched later
+      CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attr));
+      int occ = 1;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, threads, smem));
+      occ = std::max(1, occ);
+      size_t slots = (size_t)c->sm_count * occ / C;
+      if (C > 1) slots = std::max<size_t>(1, slots * 7 / 8);  // clusters cannot straddle GPCs
+      size_t n_cl = std::max<size_t>(1, std::min<size_t>(list.size(), slots) / divisor);
+      size_t bt_want = std::min<size_t>(std::max<size_t>((size_t)2048 * max_W * divisor, (size_t)4 << 20), (size_t)8 << 30);
+      size_t slab = max_fixed + bt_want;
+      while (n_cl > 1 && slab * n_cl > budget) n_cl = (n_cl + 1) / 2;
+      if (slab * n_cl > budget) slab = budget;
+      if (slab < max_fixed + 4096) return fail(c, SFC_ERR_OOM, "device workspace too small: need %zu B for one pair", max_fixed);
+      pl->slab = slab & ~(size_t)255;
+      pl->n_cl = n_cl;
+      return 0;
+    };
+    auto launch_job = [&](const uint32_t* order_dev, size_t count, int threads, int C, const Plan& pl, unsigned char* ws, uint32_t* counter,
+                          cudaStream_t st) -> int {
+      K2Params P;
+      P.pairs = (const DevPair*)c->d_pairs.p;
+      P.order = order_dev;
+      P.n = (uint32_t)count;
+      P.counter = counter;
+      P.nib = (const uint32_t*)c->d_nib.p;
+      P.scores = (int32_t*)c->d_scores.p;
+      P.status = (int32_t*)c->d_status.p;
+      P.metric = a.metric; P.x = a.x; P.o1 = a.o1; P.e1 = a.e1; P.o2 = a.o2; P.e2 = a.e2; P.match = a.match;
+      P.nM = nM; P.nG1 = nG1; P.nG2 = nG2;
+      P.slabs = ws;
+      P.slab_bytes = pl.slab;
+      P.want_cigar = c->want_cigar;
+      P.pool = (uint32_t*)c->d_pool.p;
+      P.pool_cap = pool_cap;
+      P.pool_used = (unsigned long long*)(misc + 4);
+      P.out_off = (unsigned long long*)c->d_outoff.p;
+      P.out_len = (uint32_t*)c->d_outlen.p;
+      P.cells = (unsigned long long*)(misc + 2);
+      P.win_cap = pl.win_cap;
+      P.max_score = INT_MAX / 4;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(pl.n_cl * C));
+      cfg.blockDim = dim3((unsigned)threads);
+      cfg.dynamicSmemBytes = pl.smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (a.metric == 1) CU(cudaLaunchKernelEx(&cfg, k2_align<true>, P));
+      else CU(cudaLaunchKernelEx(&cfg, k2_align<false>, P));
+      c->stats.launches++;
+      return 0;
+    };
+
+    // ---- first pass: all jobs back to back on the stream (heaviest clusters first) ----
+    // Each job owns a slice of the workspace, of the order array and its own work counter.
+    std::vector<Plan> plans(jobs.size());
+    {
+      // split the budget in proportion to demand, then allocate once
+      size_t demand_total = 0;
+      std::vector<size_t> demand(jobs.size());
+      for (size_t j = 0; j < jobs.size(); ++j) {
+        if ((rc = plan_job(jobs[j].list, jobs[j].threads, jobs[j].C, avail, 1, &plans[j]))) return rc;
+        demand[j] = plans[j].slab * plans[j].n_cl;
+        demand_total += demand[j];
+      }
+      if (demand_total > avail) {
+        for (size_t j = 0; j < jobs.size(); ++j) {
+          const size_t budget = std::max<size_t>((size_t)((double)avail * ((double)demand[j] / (double)demand_total)), plans[j].max_fixed + (1 << 20));
+          if ((rc = plan_job(jobs[j].list, jobs[j].threads, jobs[j].C, budget, 1, &plans[j]))) return rc;
+        }
+      }
+      size_t need = 0;
+      for (size_t j = 0; j < jobs.size(); ++j) need += plans[j].slab * plans[j].n_cl;
+      if ((rc = ensure(c, c->d_ws, need))) return rc;
+    }
+    CU(cudaMemsetAsync(misc + 8, 0, 32, c->stream));
+    {
+      // rewrite the K2 part of the order array job by job
+      size_t pos = k2s_begin;
+      for (auto& j : jobs) { std::copy(j.list.begin(), j.list.end(), c->h_order.begin() + pos); pos += j.list.size(); }
+      CU(cudaMemcpyAsync((uint32_t*)c->d_order.p + k2s_begin, c->h_order.data() + k2s_begin, (n - k2s_begin) * 4, cudaMemcpyHostToDevice, c->stream));
+      size_t ws_off = 0;
+      pos = k2s_begin;
+      // jobs run concurrently on their own streams (fork from / join to the ctx stream with events): cluster jobs
+      // take whole SMs first, single-CTA jobs fill whatever is free and take over as clusters drain
+      CU(cudaEventRecord(c->job_ev[6], c->stream));
+      for (size_t j = 0; j < jobs.size(); ++j) {
+        cudaStream_t st = c->job_stream[j % 6];
+        CU(cudaStreamWaitEvent(st, c->job_ev[6], 0));
+        if ((rc = launch_job((const uint32_t*)c->d_order.p + pos, jobs[j].list.size(), jobs[j].threads, jobs[j].C, plans[j],
+                             (unsigned char*)c->d_ws.p + ws_off, misc + 8 + j, st))) return rc;
+        CU(cudaEventRecord(c->job_ev[j % 6], st));
+        CU(cudaStreamWaitEvent(c->stream, c->job_ev[j % 6], 0));
+        ws_off += plans[j].slab * plans[j].n_cl;
+        pos += jobs[j].list.size();
+      }
+    }
+    // ---- escalation passes for pairs that ran out of slab (-6) or of pool (-4) ----
+    std::vector<uint32_t> retry, cur(c->h_order.begin() + k2s_begin, c->h_order.end());
+    int divisor = 1;
+    for (int pass = 0; pass < 12; ++pass) {
+      c->h_status.resize(n);
+      CU(cudaMemcpyAsync(c->h_status.data(), c->d_status.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      retry.clear();
+      bool pool_short = false;
+      for (uint32_t pi : cur) {
+        const int stt = c->h_status[pi];
+        if (stt == SFC_STATUS_OOM) retry.push_back(pi);
+        else if (stt == -4) { retry.push_back(pi); pool_short = true; }
+      }
+      if (retry.empty()) break;
+      if (divisor >= (1 << 20)) break;  // nothing left to escalate: statuses stay -6
+      c->stats.retries++;
+      if (pool_short) {
+        unsigned long long used = 0;
+        CU(cudaMemcpy(&used, misc + 4, 8, cudaMemcpyDeviceToHost));
+        DevBuf bigger;
+        const size_t new_cap = std::max<size_t>(pool_cap * 4, (size_t)used + ((size_t)1 << 22));
+        if ((rc = ensure(c, bigger, new_cap * 4))) return rc;
+        CU(cudaMemcpy(bigger.p, c->d_pool.p, std::min<size_t>((size_t)used, pool_cap) * 4, cudaMemcpyDeviceToDevice));
+        // failed reservations leave holes above the old capacity but never overlap valid runs
+        release(c->d_pool);
+        c->d_pool = bigger;
+        pool_cap = c->d_pool.cap / 4;
+      }
+      divisor *= 4;
+      Plan pl;
+      if ((rc = plan_job(retry, 512, 1, avail, divisor, &pl))) return rc;
+      if ((rc = ensure(c, c->d_ws, pl.slab * pl.n_cl))) return rc;
+      cur = retry;
+      CU(cudaMemcpyAsync((uint32_t*)c->d_order.p + k2s_begin, retry.data(), retry.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      CU(cudaMemsetAsync(misc + 8, 0, 4, c->stream));
+      if ((rc = launch_job((const uint32_t*)c->d_order.p + k2s_begin, retry.size(), 512, 1, pl, (unsigned char*)c->d_ws.p, misc + 8, c->stream))) return rc;
+      if (pl.n_cl == 1 && pl.slab >= avail - 4096 && !pool_short) divisor = 1 << 20;  // last resort was tried
     }
   }
   CU(cudaEventRecord(c->ev[4], c->stream));
