@@ -39,7 +39,7 @@ WORKLOADS = {
     "config5": dict(preset="large_indel", want_cigar=True,
                     desc="stress: 10-50 kb insertion/duplication haplotypes at 1-5% divergence"),
 }
-DEFAULT_READS = {"config2": 192, "config2_linear": 192, "config2b": 200000, "config3": 256, "config5": 8}
+DEFAULT_READS = {"config2": 1024, "config2_linear": 1024, "config2b": 200000, "config3": 512, "config5": 8}
 
 
 def make_batch(workload, n_reads, seed):

@@ -133,6 +133,14 @@ int sfc_aligner_align(sfc_aligner*, const uint8_t* pattern, size_t len, int mode
                       int32_t* score, int* has_alignment, int64_t* ref_offset,
                       uint32_t* cigar, size_t cigar_cap, size_t* n_cigar);
 
+/* ---- multi-GPU sharding helpers (host only; no collective: batches are independent) ----
+ * The unit of sharding is the SV group / breakpoint cluster, the reference's own rayon task granularity
+ * (src/joint_call/joint_call_all_samples.rs:127-142, src/refine_sv/mod.rs:861-887). */
+/* Estimated alignment work of each pair (wavefront cells), the weight both the sharder and the in-batch scheduler use. */
+int sfc_estimate_pair_work(const sfc_penalties*, const sfc_pair* pairs, size_t n_pairs, uint64_t* work);
+/* Greedy longest-processing-time assignment of groups to shards (deterministic). shard_of_group: [n_groups]. */
+int sfc_shard_plan(const uint64_t* group_work, size_t n_groups, int n_shards, uint32_t* shard_of_group);
+
 /* ---- measurement helper: integer-ALU roofline denominator (IADD3/LOP3 issue rate) ---- */
 /* Runs a dependent-chain-free INT32 micro-benchmark and returns giga-ops/s (thread-level ops). */
 int sfc_measure_int_peak(sfc_ctx*, double* gops_per_s, double* sm_clock_mhz_est);

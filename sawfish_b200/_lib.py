@@ -40,7 +40,7 @@ EXPORTS = [
     "sfc_align_batch", "sfc_batch_upload", "sfc_batch_run", "sfc_batch_download", "sfc_batch_get_stats",
     "sfc_expand_ops", "sfc_translate_cigar", "sfc_translate_rle",
     "sfc_aligner_new_consensus", "sfc_aligner_new_large_indel", "sfc_aligner_free", "sfc_aligner_set_text",
-    "sfc_aligner_align", "sfc_measure_int_peak",
+    "sfc_aligner_align", "sfc_measure_int_peak", "sfc_estimate_pair_work", "sfc_shard_plan",
 ]
 
 
@@ -92,6 +92,8 @@ def lib():
     L.sfc_aligner_align.argtypes = [vp, u8p, C.c_size_t, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int), i64p, u32p, C.c_size_t, szp]
     L.sfc_measure_int_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.sfc_estimate_pair_work.argtypes = [C.POINTER(Penalties), vp, C.c_size_t, vp]
+    L.sfc_shard_plan.argtypes = [vp, C.c_size_t, C.c_int, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("sfc_abi_version", "sfc_device_count"):

@@ -145,6 +145,8 @@ long long gap_cost(const AdjPen& a, long long L) {
   return std::min((long long)a.o1 + (long long)a.e1 * L, (long long)a.o2 + (long long)a.e2 * L);
 }
 
+double estimate_work(const AdjPen& a, double plen, double tlen, double pbf, double tbf);
+
 void init_lut_host(uint8_t* lut) {
   memset(lut, 0xFF, 256);
   const char* up = "ACGTN";
@@ -449,9 +451,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       double total = 0;
       for (size_t q = 0; q < nl; ++q) {
         const DevPair& d = c->h_pairs[c->h_order[k2l_begin + q]];
-        const double dl = std::abs((double)d.plen - (double)d.tlen);
-        const double es = (double)gap_cost(a, (long long)dl) + 0.012 * 0.5 * ((double)d.plen + d.tlen) + 8.0;
-        est[q] = es * ((double)d.pbf + d.tbf + 1.0 + 0.4 * es);
+        est[q] = estimate_work(a, d.plen, d.tlen, d.pbf, d.tbf);
         total += est[q];
       }
       int force_c = 0;
@@ -879,6 +879,38 @@ extern "C" int sfc_aligner_align(sfc_aligner* a, const uint8_t* pattern, size_t 
   if (has_alignment) *has_alignment = hm;
   if (ref_offset) *ref_offset = roff;
   if (n_cigar) *n_cigar = nc;
+  return SFC_OK;
+}
+
+// ============================================================================ sharding helpers
+namespace {
+double estimate_work(const AdjPen& a, double plen, double tlen, double pbf, double tbf) {
+  const double dl = std::abs(plen - tlen);
+  const double es = (double)gap_cost(a, (long long)dl) + 0.012 * 0.5 * (plen + tlen) + 8.0;  // expected final score
+  return es * (pbf + tbf + 1.0 + 0.4 * es);                                                   // x mean wavefront width
+}
+}  // namespace
+
+extern "C" int sfc_estimate_pair_work(const sfc_penalties* pen, const sfc_pair* pairs, size_t n, uint64_t* work) {
+  AdjPen a;
+  if (adjust_penalties(pen, &a) || (!pairs && n) || (!work && n)) return SFC_ERR_INVALID;
+  for (size_t i = 0; i < n; ++i)
+    work[i] = (uint64_t)estimate_work(a, pairs[i].pattern_len, pairs[i].text_len, pairs[i].pattern_begin_free, pairs[i].text_begin_free);
+  return SFC_OK;
+}
+
+extern "C" int sfc_shard_plan(const uint64_t* group_work, size_t n_groups, int n_shards, uint32_t* shard_of_group) {
+  if (n_shards <= 0 || (!group_work && n_groups) || (!shard_of_group && n_groups)) return SFC_ERR_INVALID;
+  std::vector<uint32_t> idx(n_groups);
+  for (size_t i = 0; i < n_groups; ++i) idx[i] = (uint32_t)i;
+  std::stable_sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return group_work[x] > group_work[y]; });
+  std::vector<unsigned long long> load((size_t)n_shards, 0);
+  for (uint32_t g : idx) {
+    int best = 0;
+    for (int s = 1; s < n_shards; ++s) if (load[s] < load[best]) best = s;
+    shard_of_group[g] = (uint32_t)best;
+    load[best] += group_work[g] + 1;
+  }
   return SFC_OK;
 }
 
