@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_PKG, "libsawfish_cuda.so")
+SO_PATH = os.environ.get("SFC_SO_PATH") or os.path.join(_PKG, "libsawfish_cuda.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 SFC_OK = 0

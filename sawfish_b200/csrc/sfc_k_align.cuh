@@ -54,6 +54,7 @@ struct K2Params {
   unsigned long long* cells;
   int win_cap;  // uint2 windows available in shared memory for both sequences together
   int max_score;
+  unsigned long long* prof;  // optional phase timers (clock64 of thread 0): [0] cell loop [1] barriers+trim [2] backtrace [3] setup
 };
 
 struct K2Range {
@@ -75,8 +76,186 @@ __device__ __forceinline__ long long k2_gap_cost(const K2Params& P, int L) {
   return a < b ? a : b;
 }
 
-template <bool AFF>
-__global__ void __launch_bounds__(512) k2_align(const K2Params P) {
+// Ring element type: int16 when both sequences are <= K2_MAX_LEN16 bases (halves the L2/HBM traffic of the rings,
+// which is what bounds the kernel), int32 otherwise.  Stored values are clamped: negative -> null, and
+// out-of-matrix insertion offsets (which only ever grow) saturate at a value that is still out of matrix.
+constexpr int K2_MAX_LEN16 = 32000;
+template <typename T> struct K2Off;
+template <> struct K2Off<int32_t> {
+  static __device__ __forceinline__ int32_t enc(int32_t v) { return v; }
+};
+template <> struct K2Off<int16_t> {
+  static __device__ __forceinline__ int16_t enc(int32_t v) { return (int16_t)(v < 0 ? -16384 : min(v, 32767)); }
+};
+
+template <typename T> struct K2Vec;
+template <> struct K2Vec<int32_t> {
+  static __device__ __forceinline__ void load(const int32_t* p, int32_t (&o)[4]) {
+    const int4 v = *reinterpret_cast<const int4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(int32_t* p, const int32_t (&o)[4]) {
+    *reinterpret_cast<int4*>(p) = make_int4(o[0], o[1], o[2], o[3]);
+  }
+};
+template <> struct K2Vec<int16_t> {
+  static __device__ __forceinline__ void load(const int16_t* p, int32_t (&o)[4]) {
+    const short4 v = *reinterpret_cast<const short4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(int16_t* p, const int32_t (&o)[4]) {
+    short4 v;
+    v.x = K2Off<int16_t>::enc(o[0]); v.y = K2Off<int16_t>::enc(o[1]); v.z = K2Off<int16_t>::enc(o[2]); v.w = K2Off<int16_t>::enc(o[3]);
+    *reinterpret_cast<short4*>(p) = v;
+  }
+};
+
+
+// Continuation of a match run that already covered its first 8-base window (rare): one more private window,
+// then warp-cooperative 256-base rounds.  Warp-uniform call; `go` selects the lanes that continue.
+__device__ __forceinline__ int k2_extend_more(const uint2* __restrict__ wp, const uint2* __restrict__ wt, int plen, int tlen,
+                                              int k, int off, bool go, int lane) {
+  bool pending = false;
+  if (go) {
+    const uint32_t x2 = window8(wp, off - k) ^ window8(wt, off);
+    if (x2) off += lead_eq(x2);
+    else { off += 8; pending = true; }
+  }
+  unsigned pm = __ballot_sync(FULL, pending);
+  while (pm) {
+    const int src = __ffs((int)pm) - 1;
+    pm &= pm - 1;
+    const int ko = __shfl_sync(FULL, k, src), ho = __shfl_sync(FULL, off, src);
+    const int adv = coop_extend(wp, wt, plen, tlen, ko, ho, lane);
+    if (lane == src) off += adv;
+  }
+  return off;
+}
+
+struct K2Rows {  // 32-bit element offsets of the source / destination ring rows of one score step
+  unsigned qMX, qMO1, qMO2, qI1E, qD1E, qI2E, qD2E, wM, wI1, wD1, wI2, wD2;
+};
+
+// One interior chunk (128 diagonals per warp, 4 per thread): every lane is active and every read of every source
+// lies inside that source's live range, so there are no guards and no predicates — straight-line code.
+template <bool AFF, bool HAS2, typename T>
+__device__ __forceinline__ void k2_fast_chunk(const T* __restrict__ R, T* __restrict__ Wr, unsigned char* __restrict__ btq,
+                                              const K2Rows& q, unsigned e0, int k0, int lane,
+                                              const uint2* __restrict__ wp, const uint2* __restrict__ wt,
+                                              int plen, int tlen, int pef, int tef, int& term_k) {
+  int32_t mx[4], m1[4], best[4];
+  uint32_t ch[4];
+  K2Vec<T>::load(R + q.qMX + e0, mx);
+  K2Vec<T>::load(R + q.qMO1 + e0, m1);
+  int32_t m1l = __shfl_up_sync(FULL, m1[3], 1), m1r = __shfl_down_sync(FULL, m1[0], 1);
+  if (lane == 0) m1l = R[q.qMO1 + e0 - 1u];
+  if (lane == 31) m1r = R[q.qMO1 + e0 + 4u];
+  int32_t ins1[4], del1[4], ins2[4], del2[4];
+  if (AFF) {
+    int32_t a1[4], d1[4];
+    K2Vec<T>::load(R + q.qI1E + e0, a1);
+    K2Vec<T>::load(R + q.qD1E + e0, d1);
+    int32_t a1l = __shfl_up_sync(FULL, a1[3], 1), d1r = __shfl_down_sync(FULL, d1[0], 1);
+    if (lane == 0) a1l = R[q.qI1E + e0 - 1u];
+    if (lane == 31) d1r = R[q.qD1E + e0 + 4u];
+    int32_t m2[4], a2[4], d2[4], m2l = WNULL, m2r = WNULL, a2l = WNULL, d2r = WNULL;
+    if (HAS2) {
+      K2Vec<T>::load(R + q.qMO2 + e0, m2);
+      K2Vec<T>::load(R + q.qI2E + e0, a2);
+      K2Vec<T>::load(R + q.qD2E + e0, d2);
+      m2l = __shfl_up_sync(FULL, m2[3], 1); m2r = __shfl_down_sync(FULL, m2[0], 1);
+      a2l = __shfl_up_sync(FULL, a2[3], 1); d2r = __shfl_down_sync(FULL, d2[0], 1);
+      if (lane == 0) { m2l = R[q.qMO2 + e0 - 1u]; a2l = R[q.qI2E + e0 - 1u]; }
+      if (lane == 31) { m2r = R[q.qMO2 + e0 + 4u]; d2r = R[q.qD2E + e0 + 4u]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int32_t i1o = j == 0 ? m1l : m1[j > 0 ? j - 1 : 0], d1o = j == 3 ? m1r : m1[j < 3 ? j + 1 : 3];
+      const int32_t i1e = j == 0 ? a1l : a1[j > 0 ? j - 1 : 0], d1e = j == 3 ? d1r : d1[j < 3 ? j + 1 : 3];
+      uint32_t c = 0;
+      const int32_t vi1 = max(i1o, i1e) + 1; if (i1e >= i1o) c |= K2_BIT_I1E;
+      const int32_t vd1 = max(d1o, d1e);     if (d1e >= d1o) c |= K2_BIT_D1E;
+      int32_t bb = vi1; uint32_t sel = K2_SEL_I1;
+      if (HAS2) {
+        const int32_t i2o = j == 0 ? m2l : m2[j > 0 ? j - 1 : 0], d2o = j == 3 ? m2r : m2[j < 3 ? j + 1 : 3];
+        const int32_t i2e = j == 0 ? a2l : a2[j > 0 ? j - 1 : 0], d2e = j == 3 ? d2r : d2[j < 3 ? j + 1 : 3];
+        const int32_t vi2 = max(i2o, i2e) + 1; if (i2e >= i2o) c |= K2_BIT_I2E;
+        const int32_t vd2 = max(d2o, d2e);     if (d2e >= d2o) c |= K2_BIT_D2E;
+        if (vi2 >= bb) { bb = vi2; sel = K2_SEL_I2; }
+        if (vd1 >= bb) { bb = vd1; sel = K2_SEL_D1; }
+        if (vd2 >= bb) { bb = vd2; sel = K2_SEL_D2; }
+        ins2[j] = vi2; del2[j] = vd2;
+      } else {
+        // piece-2 sources do not exist: ins2 = del2 = null.  The reference comparison chain still visits them
+        // (null >= null is true for the ext bits; null never wins the max), so only the ext bits are affected.
+        c |= K2_BIT_I2E | K2_BIT_D2E;
+        if (vd1 >= bb) { bb = vd1; sel = K2_SEL_D1; }
+      }
+      const int32_t mis = mx[j] + 1;
+      if (mis >= bb) { bb = mis; sel = K2_SEL_X; }
+      best[j] = bb; ch[j] = c | sel;
+      ins1[j] = vi1; del1[j] = vd1;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int32_t vi = (j == 0 ? m1l : m1[j > 0 ? j - 1 : 0]) + 1, vd = j == 3 ? m1r : m1[j < 3 ? j + 1 : 3];
+      const int32_t mis = mx[j] + 1;
+      int32_t bb = vi; uint32_t sel = K2_SEL_I1;
+      if (vd >= bb) { bb = vd; sel = K2_SEL_D1; }
+      if (mis >= bb) { bb = mis; sel = K2_SEL_X; }
+      best[j] = bb; ch[j] = sel;
+    }
+  }
+  // choice bytes and I/D rows do not depend on the extension: store them first
+  *reinterpret_cast<uint32_t*>(btq + e0) = ch[0] | (ch[1] << 8) | (ch[2] << 16) | (ch[3] << 24);
+  if (AFF) {
+    K2Vec<T>::store(Wr + q.wI1 + e0, ins1);
+    K2Vec<T>::store(Wr + q.wD1 + e0, del1);
+    if (HAS2) { K2Vec<T>::store(Wr + q.wI2 + e0, ins2); K2Vec<T>::store(Wr + q.wD2 + e0, del2); }
+  }
+  // bounds + first 8-base window of the four cells (independent chains)
+  uint32_t xw[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = k0 + j;
+    if (!k2_in_matrix(best[j], k, plen, tlen)) best[j] = WNULL;
+    const bool valid = best[j] >= 0;
+    xw[j] = window8(wp, valid ? best[j] - k : 0) ^ window8(wt, valid ? best[j] : 0);
+  }
+  bool more = false, edge = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool valid = best[j] >= 0;
+    if (valid) best[j] += xw[j] ? lead_eq(xw[j]) : 8;
+    more = more || (valid && xw[j] == 0u);
+  }
+  if (__any_sync(FULL, more)) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      best[j] = k2_extend_more(wp, wt, plen, tlen, k0 + j, best[j], best[j] >= 0 && xw[j] == 0u, lane);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) edge = edge || best[j] >= tlen || best[j] - (k0 + j) >= plen;
+  if (edge) {  // a cell touches the end of a sequence: full ends-free termination test (rare)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + j, off = best[j];
+      if (off >= 0) {
+        const int v = off - k;
+        if ((off >= tlen && plen - v <= pef) || (v >= plen && tlen - off <= tef)) term_k = min(term_k, k);
+      }
+    }
+  }
+  K2Vec<T>::store(Wr + q.wM + e0, best);
+}
+
+template <bool AFF, typename T>
+#ifndef K2_LB_T
+#define K2_LB_T 512
+#define K2_LB_B 1
+#endif
+__global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
   extern __shared__ __align__(16) unsigned char k2_smem[];
   // A pair is aligned by one CTA, or by a thread-block cluster of C CTAs (C SMs) for long haplotypes: the
   // CTAs of a cluster stride the diagonals of each wavefront together, share the rings / choice bytes in
@@ -93,9 +272,12 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
   unsigned char* slab = P.slabs + (size_t)(blockIdx.x / C) * P.slab_bytes;
   int* misc0 = C > 1 ? cluster.map_shared_rank(misc, 0) : misc;  // rank 0's copy: work index + terminating diagonal
   unsigned long long cells_acc = 0;
+  long long t_cells = 0, t_sync = 0, t_bt = 0, t_setup = 0, t_mark = clock64();
+#define K2_TICK(acc) do { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; } while (0)
 
   for (;;) {
     csync();
+    K2_TICK(t_bt);
     if (crank == 0 && tid == 0) { misc[0] = (int)atomicAdd(P.counter, 1u); misc[1] = INT_MAX; }
     csync();
     const uint32_t wi = (uint32_t)misc0[0];
@@ -107,11 +289,11 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
     uint2* wp = win;
     uint2* wt = win + nwp;
     // ---- carve the slab ----
-    const int Wp = plen + tlen + 5, kbase = plen + 2;
+    const int Wp = (plen + tlen + 16 + 7) & ~7, kbase = plen + 2;  // rows are vector-aligned and have slack for the edge groups
     long long scap_ll = k2_gap_cost(P, plen) + k2_gap_cost(P, tlen) + 1;
     if (scap_ll > P.max_score) scap_ll = P.max_score;
     const int S_cap = (int)scap_ll;
-    const size_t ring_bytes = ((size_t)nslots * Wp * 4 + 15) & ~(size_t)15;
+    const size_t ring_bytes = ((size_t)nslots * Wp * sizeof(T) + 15) & ~(size_t)15;
     const size_t rowoff_bytes = (((size_t)S_cap + 1) * 8 + 15) & ~(size_t)15;
     const size_t rowlo_bytes = (((size_t)S_cap + 1) * 4 + 15) & ~(size_t)15;
     const size_t E_cap = (size_t)plen + tlen + 8;
@@ -124,7 +306,7 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
       if (crank == 0 && tid == 0) { P.scores[pi] = 0; P.status[pi] = res_status; P.out_len[pi] = 0; P.out_off[pi] = 0; }
       continue;
     }
-    int32_t* rings = reinterpret_cast<int32_t*>(slab);
+    T* rings = reinterpret_cast<T*>(slab);
     unsigned long long* rowoff = reinterpret_cast<unsigned long long*>(slab + ring_bytes);
     int* rowlo = reinterpret_cast<int*>(slab + ring_bytes + rowoff_bytes);
     uint32_t* tmp_b = reinterpret_cast<uint32_t*>(slab + ring_bytes + rowoff_bytes + rowlo_bytes);
@@ -162,6 +344,7 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
 
     int s = 0, end_k = 0;
     bool done = false;
+    K2_TICK(t_setup);
     for (;; ++s) {
       if (s > S_cap) { res_status = -7; break; }
       // ---- source wavefronts ----
@@ -195,7 +378,9 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
         continue;
       }
       const int width = hi - lo + 1;
-      if (bt_used + (unsigned long long)width > bt_cap) { res_status = -6; break; }
+      // choice bytes are stored per 4-diagonal group: row s covers diagonals [4*g_lo - kbase, 4*g_hi + 3 - kbase]
+      const unsigned long long bt_row_bytes = 4ull * (unsigned long long)((((hi + kbase) >> 2) - ((lo + kbase) >> 2)) + 1);
+      if (bt_used + bt_row_bytes > bt_cap) { res_status = -6; break; }
       const bool has2 = AFF && (MO2.any() || I2E.any() || D2E.any());
       // interior where every read of every (existing-piece) source is in range
       int ilo, ihi;
@@ -213,105 +398,190 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
         }
         if (!ok || s == 0) { ilo = 1; ihi = 0; }
       }
-      const int32_t* __restrict__ R = rings;
-      const int qMX = slot_of(K2_C_M, max(s_mx, 0)) * Wp + kbase, qMO1 = slot_of(K2_C_M, max(s_o1, 0)) * Wp + kbase;
-      const int qMO2 = slot_of(K2_C_M, max(s_o2, 0)) * Wp + kbase;
-      const int qI1E = slot_of(K2_C_I1, max(s_e1, 0)) * Wp + kbase, qD1E = slot_of(K2_C_D1, max(s_e1, 0)) * Wp + kbase;
-      const int qI2E = slot_of(K2_C_I2, max(s_e2, 0)) * Wp + kbase, qD2E = slot_of(K2_C_D2, max(s_e2, 0)) * Wp + kbase;
-      const int wM = slot_of(K2_C_M, s) * Wp + kbase, wI1 = slot_of(K2_C_I1, s) * Wp + kbase, wD1 = slot_of(K2_C_D1, s) * Wp + kbase;
-      const int wI2 = slot_of(K2_C_I2, s) * Wp + kbase, wD2 = slot_of(K2_C_D2, s) * Wp + kbase;
-      unsigned char* btrow = bt + bt_used - lo;  // indexed by k
+      const T* __restrict__ R = rings;
+      // unsigned element offsets of the row starts (row r, diagonal k lives at r*Wp + kbase + k >= 0)
+      const unsigned uWp = (unsigned)Wp;
+      const unsigned qMX = (unsigned)slot_of(K2_C_M, max(s_mx, 0)) * uWp, qMO1 = (unsigned)slot_of(K2_C_M, max(s_o1, 0)) * uWp;
+      const unsigned qMO2 = (unsigned)slot_of(K2_C_M, max(s_o2, 0)) * uWp;
+      const unsigned qI1E = (unsigned)slot_of(K2_C_I1, max(s_e1, 0)) * uWp, qD1E = (unsigned)slot_of(K2_C_D1, max(s_e1, 0)) * uWp;
+      const unsigned qI2E = (unsigned)slot_of(K2_C_I2, max(s_e2, 0)) * uWp, qD2E = (unsigned)slot_of(K2_C_D2, max(s_e2, 0)) * uWp;
+      const unsigned wM = (unsigned)slot_of(K2_C_M, s) * uWp, wI1 = (unsigned)slot_of(K2_C_I1, s) * uWp, wD1 = (unsigned)slot_of(K2_C_D1, s) * uWp;
+      const unsigned wI2 = (unsigned)slot_of(K2_C_I2, s) * uWp, wD2 = (unsigned)slot_of(K2_C_D2, s) * uWp;
+      unsigned char* btrow = bt + bt_used;  // byte index = (k + kbase) - 4*g_lo
       const int cMX = MX.cnt(), cMO1 = MO1.cnt(), cMO2 = MO2.cnt(), cI1E = I1E.cnt(), cD1E = D1E.cnt(),
                 cI2E = I2E.cnt(), cD2E = D2E.cnt();
       int term_k = INT_MAX;
 
-      for (int kb = lo + (crank * NW + warp) * 32; kb <= hi; kb += C * NT) {
-        const int k = kb + lane;
-        const bool act = k <= hi;
-        int32_t best = WNULL, ins1 = WNULL, ins2 = WNULL, del1 = WNULL, del2 = WNULL;
-        uint32_t ch = 0;
+      // ---- cell loop: each thread owns a group of 4 consecutive diagonals (one 8/16-byte vector per ring row),
+      // a warp a chunk of 128; the k-1 / k+1 neighbours come from the adjacent lanes by shuffle ----
+      const int g_lo = (lo + kbase) >> 2, g_hi = (hi + kbase) >> 2;
+      auto in_rng = [](int k, const K2Range& r, int cnt) -> bool { return (unsigned)(k - r.lo) < (unsigned)cnt; };
+      // vector of a row at my group, plus the element just left / right of it (from the neighbouring lanes)
+      auto load_row = [&](unsigned q, unsigned e0, bool ok, bool last_group, bool want_l, bool want_r, int32_t (&v)[4], int32_t& left, int32_t& right) {
+        v[0] = v[1] = v[2] = v[3] = WNULL;
+        if (ok) K2Vec<T>::load(R + q + e0, v);
+        if (want_l) {
+          left = __shfl_up_sync(FULL, v[3], 1);
+          if (lane == 0) left = (ok && e0 >= 1u) ? (int32_t)R[q + e0 - 1u] : WNULL;
+        }
+        if (want_r) {
+          right = __shfl_down_sync(FULL, v[0], 1);
+          if (lane == 31 || last_group) right = ok ? (int32_t)R[q + e0 + 4u] : WNULL;  // lane+1 holds nothing useful
+        }
+      };
+      K2Rows rows;
+      rows.qMX = qMX; rows.qMO1 = qMO1; rows.qMO2 = qMO2; rows.qI1E = qI1E; rows.qD1E = qD1E; rows.qI2E = qI2E; rows.qD2E = qD2E;
+      rows.wM = wM; rows.wI1 = wI1; rows.wD1 = wD1; rows.wI2 = wI2; rows.wD2 = wD2;
+      unsigned char* btq = btrow - ((size_t)g_lo << 2);  // indexed by the element offset e = k + kbase
+      const int flo = max(ilo, lo), fhi = min(ihi, hi);
+      for (int gb = g_lo + (crank * NW + warp) * 32; gb <= g_hi; gb += C * NW * 32) {
+        const int g = gb + lane;
+        const bool gact = g <= g_hi;
+        const unsigned e0 = (unsigned)g << 2;
+        const int k0 = (int)e0 - kbase;
+        if (s > 0 && (gb << 2) - kbase >= flo && (gb << 2) - kbase + 127 <= fhi) {  // interior chunk
+          if (has2) k2_fast_chunk<AFF, true, T>(R, rings, btq, rows, e0, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+          else k2_fast_chunk<AFF, false, T>(R, rings, btq, rows, e0, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+          continue;
+        }
+        int32_t best[4], ins1[4], ins2[4], del1[4], del2[4];
+        uint32_t ch[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { best[j] = ins1[j] = ins2[j] = del1[j] = del2[j] = WNULL; ch[j] = 0; }
         if (s == 0) {
-          if (act) best = max(k, 0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const int k = k0 + j; if (k >= lo && k <= hi) best[j] = max(k, 0); }
         } else {
-          int32_t mx, i1o, d1o, i1e = WNULL, d1e = WNULL, i2o = WNULL, d2o = WNULL, i2e = WNULL, d2e = WNULL;
-          if (kb >= ilo && kb + 31 <= ihi) {
-            mx = R[qMX + k]; i1o = R[qMO1 + k - 1]; d1o = R[qMO1 + k + 1];
-            if (AFF) {
-              i1e = R[qI1E + k - 1]; d1e = R[qD1E + k + 1];
-              if (has2) { i2o = R[qMO2 + k - 1]; d2o = R[qMO2 + k + 1]; i2e = R[qI2E + k - 1]; d2e = R[qD2E + k + 1]; }
+          const int kA = (gb << 2) - kbase, kB = kA + 127;
+          const bool fast = kA >= max(ilo, lo) && kB <= min(ihi, hi);
+          const bool lastg = (g == g_hi);
+          int32_t mx[4], m1[4], m1l, m1r, a1[4], a1l, d1[4], d1r, dummy = 0;
+          int32_t m2[4], m2l = WNULL, m2r = WNULL, a2[4], a2l = WNULL, d2[4], d2r = WNULL;
+          load_row(qMX, e0, gact, lastg, false, false, mx, dummy, dummy);
+          load_row(qMO1, e0, gact, lastg, true, true, m1, m1l, m1r);
+          if (AFF) {
+            load_row(qI1E, e0, gact, lastg, true, false, a1, a1l, dummy);
+            load_row(qD1E, e0, gact, lastg, false, true, d1, dummy, d1r);
+            if (has2) {
+              load_row(qMO2, e0, gact, lastg, true, true, m2, m2l, m2r);
+              load_row(qI2E, e0, gact, lastg, true, false, a2, a2l, dummy);
+              load_row(qD2E, e0, gact, lastg, false, true, d2, dummy, d2r);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) m2[j] = a2[j] = d2[j] = WNULL;
             }
           } else {
-            mx = k2_guard(R + qMX, k, MX.lo, cMX);
-            i1o = k2_guard(R + qMO1, k - 1, MO1.lo, cMO1);
-            d1o = k2_guard(R + qMO1, k + 1, MO1.lo, cMO1);
-            if (AFF) {
-              i1e = k2_guard(R + qI1E, k - 1, I1E.lo, cI1E);
-              d1e = k2_guard(R + qD1E, k + 1, D1E.lo, cD1E);
-              if (has2) {
-                i2o = k2_guard(R + qMO2, k - 1, MO2.lo, cMO2);
-                d2o = k2_guard(R + qMO2, k + 1, MO2.lo, cMO2);
-                i2e = k2_guard(R + qI2E, k - 1, I2E.lo, cI2E);
-                d2e = k2_guard(R + qD2E, k + 1, D2E.lo, cD2E);
+            a1l = d1r = WNULL;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a1[j] = d1[j] = m2[j] = a2[j] = d2[j] = WNULL;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            int32_t vmx = mx[j];
+            int32_t i1o = j == 0 ? m1l : m1[j > 0 ? j - 1 : 0], d1o = j == 3 ? m1r : m1[j < 3 ? j + 1 : 3];
+            int32_t i1e = j == 0 ? a1l : a1[j > 0 ? j - 1 : 0], d1e = j == 3 ? d1r : d1[j < 3 ? j + 1 : 3];
+            int32_t i2o = j == 0 ? m2l : m2[j > 0 ? j - 1 : 0], d2o = j == 3 ? m2r : m2[j < 3 ? j + 1 : 3];
+            int32_t i2e = j == 0 ? a2l : a2[j > 0 ? j - 1 : 0], d2e = j == 3 ? d2r : d2[j < 3 ? j + 1 : 3];
+            if (!fast) {  // boundary chunk: every read is checked against its source wavefront's live range
+              const bool act = k >= lo && k <= hi;
+              vmx = (act && in_rng(k, MX, cMX)) ? vmx : WNULL;
+              i1o = (act && in_rng(k - 1, MO1, cMO1)) ? i1o : WNULL;
+              d1o = (act && in_rng(k + 1, MO1, cMO1)) ? d1o : WNULL;
+              if (AFF) {
+                i1e = (act && in_rng(k - 1, I1E, cI1E)) ? i1e : WNULL;
+                d1e = (act && in_rng(k + 1, D1E, cD1E)) ? d1e : WNULL;
+                i2o = (act && in_rng(k - 1, MO2, cMO2)) ? i2o : WNULL;
+                d2o = (act && in_rng(k + 1, MO2, cMO2)) ? d2o : WNULL;
+                i2e = (act && in_rng(k - 1, I2E, cI2E)) ? i2e : WNULL;
+                d2e = (act && in_rng(k + 1, D2E, cD2E)) ? d2e : WNULL;
               }
             }
-          }
-          const int32_t mis = mx + 1;
-          if (AFF) {
-            ins1 = max(i1o, i1e) + 1; if (i1e >= i1o) ch |= K2_BIT_I1E;
-            ins2 = max(i2o, i2e) + 1; if (i2e >= i2o) ch |= K2_BIT_I2E;
-            del1 = max(d1o, d1e);     if (d1e >= d1o) ch |= K2_BIT_D1E;
-            del2 = max(d2o, d2e);     if (d2e >= d2o) ch |= K2_BIT_D2E;
-            best = ins1; uint32_t sel = K2_SEL_I1;
-            if (ins2 >= best) { best = ins2; sel = K2_SEL_I2; }
-            if (del1 >= best) { best = del1; sel = K2_SEL_D1; }
-            if (del2 >= best) { best = del2; sel = K2_SEL_D2; }
-            if (mis >= best) { best = mis; sel = K2_SEL_X; }
-            ch |= sel;
-          } else {
-            const int32_t ins = i1o + 1, del = d1o;
-            best = ins; ch = K2_SEL_I1;
-            if (del >= best) { best = del; ch = K2_SEL_D1; }
-            if (mis >= best) { best = mis; ch = K2_SEL_X; }
-          }
-        }
-        if (!k2_in_matrix(best, k, plen, tlen)) best = WNULL;
-        // ---- extend M along matches ----
-        int off = best;
-        bool pending = false;
-        if (best >= 0) {
-          const int v = off - k;
-          uint32_t xw = window8(wp, v) ^ window8(wt, off);
-          if (xw) off += lead_eq(xw);
-          else {
-            off += 8;
-            xw = window8(wp, v + 8) ^ window8(wt, off);
-            if (xw) off += lead_eq(xw);
-            else { off += 8; pending = true; }
-          }
-        }
-        unsigned pm = __ballot_sync(FULL, pending);
-        while (pm) {
-          const int src = __ffs((int)pm) - 1;
-          pm &= pm - 1;
-          const int ko = __shfl_sync(FULL, k, src), ho = __shfl_sync(FULL, off, src);
-          const int adv = coop_extend(wp, wt, plen, tlen, ko, ho, lane);
-          if (lane == src) off += adv;
-        }
-        if (best >= 0) {
-          const int v = off - k;
-          if ((off >= tlen && plen - v <= pr.pef) || (v >= plen && tlen - off <= pr.tef)) term_k = min(term_k, k);
-        }
-        if (act) {
-          rings[wM + k] = off;  // off == WNULL when the cell is null
-          if (s > 0) {
-            btrow[k] = (unsigned char)ch;
+            const int32_t mis = vmx + 1;
             if (AFF) {
-              rings[wI1 + k] = ins1; rings[wD1 + k] = del1;
-              if (has2) { rings[wI2 + k] = ins2; rings[wD2 + k] = del2; }
+              uint32_t c = 0;
+              const int32_t vi1 = max(i1o, i1e) + 1; if (i1e >= i1o) c |= K2_BIT_I1E;
+              const int32_t vi2 = max(i2o, i2e) + 1; if (i2e >= i2o) c |= K2_BIT_I2E;
+              const int32_t vd1 = max(d1o, d1e);     if (d1e >= d1o) c |= K2_BIT_D1E;
+              const int32_t vd2 = max(d2o, d2e);     if (d2e >= d2o) c |= K2_BIT_D2E;
+              int32_t bb = vi1; uint32_t sel = K2_SEL_I1;
+              if (vi2 >= bb) { bb = vi2; sel = K2_SEL_I2; }
+              if (vd1 >= bb) { bb = vd1; sel = K2_SEL_D1; }
+              if (vd2 >= bb) { bb = vd2; sel = K2_SEL_D2; }
+              if (mis >= bb) { bb = mis; sel = K2_SEL_X; }
+              best[j] = bb; ch[j] = c | sel;
+              ins1[j] = vi1; ins2[j] = vi2; del1[j] = vd1; del2[j] = vd2;
+            } else {
+              const int32_t vi = i1o + 1, vd = d1o;
+              int32_t bb = vi; uint32_t sel = K2_SEL_I1;
+              if (vd >= bb) { bb = vd; sel = K2_SEL_D1; }
+              if (mis >= bb) { bb = mis; sel = K2_SEL_X; }
+              best[j] = bb; ch[j] = sel;
+            }
+          }
+        }
+        // ---- bounds, extension along matches, termination test ----
+        // First 8-base window of all four cells as straight-line code (independent LDS/SHF/XOR chains overlap);
+        // a cell that matches all 8 bases (1 in 65k on unrelated diagonals) takes the slow continuation below.
+        uint32_t xw[4];
+        bool more = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + j;
+          if (!k2_in_matrix(best[j], k, plen, tlen)) best[j] = WNULL;
+          const bool valid = best[j] >= 0;
+          xw[j] = window8(wp, valid ? best[j] - k : 0) ^ window8(wt, valid ? best[j] : 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool valid = best[j] >= 0;
+          const int n = xw[j] ? lead_eq(xw[j]) : 8;
+          if (valid) best[j] += n;
+          more = more || (valid && xw[j] == 0u);
+        }
+        if (__any_sync(FULL, more)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            int off = best[j];
+            bool pending = false;
+            if (off >= 0 && xw[j] == 0u) {  // second private window, then warp-cooperative rounds
+              const uint32_t x2 = window8(wp, off - k) ^ window8(wt, off);
+              if (x2) off += lead_eq(x2);
+              else { off += 8; pending = true; }
+            }
+            unsigned pm = __ballot_sync(FULL, pending);
+            while (pm) {
+              const int src = __ffs((int)pm) - 1;
+              pm &= pm - 1;
+              const int ko = __shfl_sync(FULL, k, src), ho = __shfl_sync(FULL, off, src);
+              const int adv = coop_extend(wp, wt, plen, tlen, ko, ho, lane);
+              if (lane == src) off += adv;
+            }
+            best[j] = off;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + j, off = best[j];
+          if (off >= 0) {
+            const int v = off - k;
+            if ((off >= tlen && plen - v <= pr.pef) || (v >= plen && tlen - off <= pr.tef)) term_k = min(term_k, k);
+          }
+        }
+        if (gact) {
+          K2Vec<T>::store(rings + wM + e0, best);
+          if (s > 0) {
+            *reinterpret_cast<uint32_t*>(btrow + (e0 - ((unsigned)g_lo << 2))) = ch[0] | (ch[1] << 8) | (ch[2] << 16) | (ch[3] << 24);
+            if (AFF) {
+              K2Vec<T>::store(rings + wI1 + e0, ins1);
+              K2Vec<T>::store(rings + wD1 + e0, del1);
+              if (has2) { K2Vec<T>::store(rings + wI2 + e0, ins2); K2Vec<T>::store(rings + wD2 + e0, del2); }
             }
           }
         }
       }
+      K2_TICK(t_cells);
       // ---- barrier 1: rows of score s complete; did any diagonal terminate? ----
       term_k = warp_min(term_k);
       if (term_k != INT_MAX && lane == 0) atomicMin(term_slot, term_k);
@@ -319,7 +589,7 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
       const int tk = *term_slot;
       if (tk != INT_MAX) {
         end_k = tk; done = true;
-        if (crank == 0 && tid == 0) { rowoff[s] = bt_used; rowlo[s] = lo; cells_acc += (unsigned long long)width; }
+        if (crank == 0 && tid == 0) { rowoff[s] = bt_used; rowlo[s] = (((lo + kbase) >> 2) << 2) - kbase; cells_acc += (unsigned long long)width; }
         break;
       }
       // ---- trim every component to its first / last in-matrix diagonal (metadata only) ----
@@ -333,19 +603,19 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
             if ((c == K2_C_I2 || c == K2_C_D2) && !has2) {
               // piece-2 wavefronts do not exist yet
             } else {
-              const int q = (c == K2_C_M ? wM : c == K2_C_I1 ? wI1 : c == K2_C_D1 ? wD1 : c == K2_C_I2 ? wI2 : wD2);
+              const unsigned q = (c == K2_C_M ? wM : c == K2_C_I1 ? wI1 : c == K2_C_D1 ? wD1 : c == K2_C_I2 ? wI2 : wD2) + (unsigned)kbase;
               bool got = false;
               if (!side) {
                 for (int base = lo; base <= hi && !got; base += 32) {
                   const int k = base + lane;
-                  const bool inm = (k <= hi) && k2_in_matrix(rings[q + k], k, plen, tlen);
+                  const bool inm = (k <= hi) && k2_in_matrix(rings[q + (unsigned)k], k, plen, tlen);
                   const unsigned b = __ballot_sync(FULL, inm);
                   if (b) { found = base + __ffs((int)b) - 1; got = true; }
                 }
               } else {
                 for (int base = hi; base >= lo && !got; base -= 32) {
                   const int k = base - lane;
-                  const bool inm = (k >= lo) && k2_in_matrix(rings[q + k], k, plen, tlen);
+                  const bool inm = (k >= lo) && k2_in_matrix(rings[q + (unsigned)k], k, plen, tlen);
                   const unsigned b = __ballot_sync(FULL, inm);
                   if (b) { found = base - (__ffs((int)b) - 1); got = true; }
                 }
@@ -357,17 +627,19 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
             else meta[2 * sl + side] = found;
           }
         }
-        if (crank == 0 && tid == 0) { rowoff[s] = bt_used; rowlo[s] = lo; cells_acc += (unsigned long long)width; }
+        if (crank == 0 && tid == 0) { rowoff[s] = bt_used; rowlo[s] = (((lo + kbase) >> 2) << 2) - kbase; cells_acc += (unsigned long long)width; }
       }
-      if (s > 0) bt_used += (unsigned long long)width;
+      if (s > 0) bt_used += bt_row_bytes;
       csync();  // barrier 2: metadata of score s visible
+      K2_TICK(t_sync);
     }
 
+    K2_TICK(t_sync);
     // ---- backtrace (warp 0): choice walk to score 0, then forward replay ----
     if (done) {
       csync();  // rowoff/rowlo/bt/oM of the last step visible to warp 0 of rank 0
       if (crank == 0 && warp == 0) {
-        const int32_t* oM = rings + (size_t)slot_of(K2_C_M, s) * Wp + kbase;
+        const T* oM = rings + (size_t)slot_of(K2_C_M, s) * Wp + kbase;
         const int end_off = oM[end_k];
         int k0 = 0, nb = 0, bad = 0;
         if (lane == 0) {
@@ -485,6 +757,12 @@ __global__ void __launch_bounds__(512) k2_align(const K2Params P) {
     }
   }
   if (crank == 0 && tid == 0 && cells_acc) atomicAdd(P.cells, cells_acc);
+  if (tid == 0 && P.prof) {
+    K2_TICK(t_bt);
+    atomicAdd(P.prof + 0, (unsigned long long)t_cells); atomicAdd(P.prof + 1, (unsigned long long)t_sync);
+    atomicAdd(P.prof + 2, (unsigned long long)t_bt); atomicAdd(P.prof + 3, (unsigned long long)t_setup);
+  }
+#undef K2_TICK
 }
 
 }  // namespace sfc

@@ -373,6 +373,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
   CU(cudaEventRecord(c->ev[3], c->stream));
   CU(cudaMemcpyAsync(c->d_order.p, c->h_order.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemsetAsync(misc, 0, 64, c->stream));  // counters, cells, pool_used (not the bad-symbol flag)
+  CU(cudaMemsetAsync(misc + 40, 0, 32, c->stream));  // optional phase timers
   c->stats.h2d_bytes += n * 4;
 
   // ---- K1 launches ----
@@ -437,9 +438,12 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     const int nM = (a.metric == 1 ? std::max(a.x, std::max(a.o1 + a.e1, a.o2 + a.e2)) : lookL) + 1;
     const int nG1 = a.e1 + 1, nG2 = a.e2 + 1;
     const int nslots = a.metric == 1 ? nM + 2 * nG1 + 2 * nG2 : nM;
-    const void* kfn = a.metric == 1 ? (const void*)k2_align<true> : (const void*)k2_align<false>;
 
     struct Job { std::vector<uint32_t> list; int threads; int C; };
+    auto kernel_of = [&](bool wide) -> const void* {
+      if (a.metric == 1) return wide ? (const void*)k2_align<true, int32_t> : (const void*)k2_align<true, int16_t>;
+      return wide ? (const void*)k2_align<false, int32_t> : (const void*)k2_align<false, int16_t>;
+    };
     std::vector<Job> jobs;
     // small pairs: one 128-thread CTA each
     if (k2l_begin > k2s_begin) jobs.push_back(Job{std::vector<uint32_t>(c->h_order.begin() + k2s_begin, c->h_order.begin() + k2l_begin), 128, 1});
@@ -470,22 +474,29 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
         if (tmp[ci].empty()) continue;
         std::stable_sort(tmp[ci].begin(), tmp[ci].end(), [](const std::pair<double, uint32_t>& x, const std::pair<double, uint32_t>& y) { return x.first > y.first; });
         Job j; j.threads = 512; j.C = 1 << ci;
+        if (const char* e = getenv("SFC_K2_THREADS")) j.threads = std::max(64, std::min(K2_LB_T, atoi(e)));  // experiment knob
         for (auto& t : tmp[ci]) j.list.push_back(t.second);
         jobs.push_back(std::move(j));
       }
     }
 
     // size one job's launch: returns grid (in clusters), slab bytes, shared bytes, win_cap
-    struct Plan { size_t n_cl, slab, smem, max_fixed; int win_cap; };
+    struct Plan { size_t n_cl, slab, smem, max_fixed; int win_cap; bool wide; };
     size_t smem_attr = 0;
     auto plan_job = [&](const std::vector<uint32_t>& list, int threads, int C, size_t budget, int divisor, Plan* pl) -> int {
       size_t max_fixed = 0, max_win = 0, max_W = 0;
+      bool wide = false;
+      for (uint32_t pi : list) wide = wide || c->h_pairs[pi].plen > K2_MAX_LEN16 || c->h_pairs[pi].tlen > K2_MAX_LEN16;
+      if (getenv("SFC_K2_WIDE")) wide = true;
+      pl->wide = wide;
+      const size_t esz = wide ? 4 : 2;
+      const void* kfn = kernel_of(wide);
       for (uint32_t pi : list) {
         const DevPair& d = c->h_pairs[pi];
-        const size_t Wp = (size_t)d.plen + d.tlen + 5;
+        const size_t Wp = ((size_t)d.plen + d.tlen + 16 + 7) & ~(size_t)7;
         long long scap = gap_cost(a, d.plen) + gap_cost(a, d.tlen) + 1;
         scap = std::min<long long>(scap, INT_MAX / 4);
-        const size_t fixed = (size_t)nslots * Wp * 4 + ((size_t)scap + 1) * 12 + 2 * (((size_t)d.plen + d.tlen + 8) * 4) + 256;
+        const size_t fixed = (size_t)nslots * Wp * esz + ((size_t)scap + 1) * 12 + 2 * (((size_t)d.plen + d.tlen + 8) * 4) + 256;
         max_fixed = std::max(max_fixed, fixed);
         max_win = std::max(max_win, (size_t)(d.plen >> 3) + (d.tlen >> 3) + 2);
         max_W = std::max(max_W, Wp);
@@ -501,6 +512,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       occ = std::max(1, occ);
       size_t slots = (size_t)c->sm_count * occ / C;
       if (C > 1) slots = std::max<size_t>(1, slots * 7 / 8);  // clusters cannot straddle GPCs
+      if (const char* e = getenv("SFC_K2_SLOT_DIV")) slots = std::max<size_t>(1, slots / std::max(1, atoi(e)));  // experiment knob
       size_t n_cl = std::max<size_t>(1, std::min<size_t>(list.size(), slots) / divisor);
       size_t bt_want = std::min<size_t>(std::max<size_t>((size_t)2048 * max_W * divisor, (size_t)4 << 20), (size_t)8 << 30);
       size_t slab = max_fixed + bt_want;
@@ -534,6 +546,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       P.cells = (unsigned long long*)(misc + 2);
       P.win_cap = pl.win_cap;
       P.max_score = INT_MAX / 4;
+      P.prof = getenv("SFC_K2_PROF") ? (unsigned long long*)(misc + 40) : nullptr;
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)(pl.n_cl * C));
       cfg.blockDim = dim3((unsigned)threads);
@@ -544,8 +557,11 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      if (a.metric == 1) CU(cudaLaunchKernelEx(&cfg, k2_align<true>, P));
-      else CU(cudaLaunchKernelEx(&cfg, k2_align<false>, P));
+      if (a.metric == 1) {
+        if (pl.wide) CU(cudaLaunchKernelEx(&cfg, k2_align<true, int32_t>, P)); else CU(cudaLaunchKernelEx(&cfg, k2_align<true, int16_t>, P));
+      } else {
+        if (pl.wide) CU(cudaLaunchKernelEx(&cfg, k2_align<false, int32_t>, P)); else CU(cudaLaunchKernelEx(&cfg, k2_align<false, int16_t>, P));
+      }
       c->stats.launches++;
       return 0;
     };
@@ -667,6 +683,11 @@ extern "C" int sfc_batch_download(sfc_ctx* c, int32_t* scores, int32_t* status, 
   memcpy(&cells, h_misc + 2, 8);
   memcpy(&pool_used, h_misc + 4, 8);
   c->stats.cells = cells;
+  if (getenv("SFC_K2_PROF")) {
+    unsigned long long pr[4];
+    memcpy(pr, h_misc + 40, 32);
+    fprintf(stderr, "[k2 prof] cycles of thread 0 summed over CTAs: cells %.3e  barriers+trim %.3e  backtrace+fetch %.3e  setup %.3e\n", (double)pr[0], (double)pr[1], (double)pr[2], (double)pr[3]);
+  }
   if (h_misc[32]) return fail(c, SFC_ERR_UNSUPPORTED, "sequence symbol outside {A,C,G,T,N,a,c,g,t,n}");
   int ret = SFC_OK;
   if (c->want_cigar) {
