@@ -5,17 +5,23 @@
 // called per read x breakend x registration x allele at src/score_sv/mod.rs:837-901 where only the
 // score is consumed (src/score_sv/mod.rs:702).
 //
-// Mapping: one group of WPP warps per pair (WPP = 1 for score_sv-sized flanks), persistent CTAs
-// pulling pairs from a global work counter.  The M-wavefront ring (depth max(x',i')+1) and both
-// sequences (4-bit, overlapped 8-byte windows) live in shared memory.  Each wavefront cell is one
-// 32-bit word:  [31] null/sign | [30:16] offset h | [15:14] predecessor-type | [13:0] k0 + 8192
+// Mapping: one group of WPP warps per pair, persistent groups pulling pairs from a global work counter.
+// The M-wavefront ring (depth max(x',i')+1) and both sequences (4-bit, overlapped 8-byte windows) live in
+// shared memory.  Each wavefront cell is one 32-bit word:
+//     [31] null/sign | [30:16] offset h | [15:14] predecessor-type | [13:0] k0 + 8192
 // so that ONE signed max over the three candidates reproduces WFA2's backtrace tie-break
 // (mismatch > deletion > insertion on equal offsets) while carrying k0, the diagonal on which the
 // winning path left wavefront 0 — needed because the reported score is taken over the non-free
 // part of the alignment only (pinned by src/wfa2_utils.rs:294-308).
-// Reads of source wavefronts are range-guarded from per-wavefront (lo,hi) metadata, so the ring
-// never needs initialising or clearing; wavefront trimming (first/last in-matrix diagonal) is
-// metadata only.  Integer-ALU bound; no tensor cores (integer DP).
+//
+// Each thread owns 4 consecutive diagonals per iteration (one LDS.128 per source row, one STS.128 out) and
+// runs recurrence, bounds and the first 8-base extend window of the four cells as straight-line code, so
+// the LDS/funnel-shift/XOR/FLO chains of four cells overlap.  Reads of source wavefronts are range-guarded
+// from per-wavefront (lo,hi) metadata, so the ring never needs initialising or clearing.  With a single
+// component, wavefront trimming only ever removes null cells, so it is not performed: the live range is the
+// computed range clamped to the matrix diagonals, and the only per-score reduction is "did a diagonal
+// terminate" (one barrier with OR-reduction for multi-warp groups).
+// Integer-ALU / shared-memory-latency bound; no tensor cores (integer DP).
 #pragma once
 #include "sfc_device.cuh"
 
@@ -39,22 +45,27 @@ struct K1Params {
   int32_t* status;
   int x, ip, match;  // adjusted mismatch / indel penalties, original match score (<= 0)
   int rd;            // ring depth = max(x, ip) + 1
-  int wcap;          // cells per ring row (>= max(plen+tlen) + 5)
+  int wcap;          // cells per ring row (multiple of 4, >= max(plen+tlen) + 12)
   int win_cap;       // uint2 windows reserved per sequence
   int group_bytes;   // shared bytes per group
   int max_score;
   unsigned long long* cells;
 };
 
+// Group synchronisation.  WPP == 1: the group is a warp.  WPP >= 2: the host launches exactly one group per
+// block, so the group barrier is the block barrier (barrier 0) — a dynamic named-barrier id would make ptxas
+// reserve all 16 barriers per block and cap residency at 4 blocks per SM.
 template <int WPP>
-__device__ __forceinline__ void k1_gsync(int group) {
+__device__ __forceinline__ void k1_gsync(int) {
   if (WPP == 1) __syncwarp();
-  else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(WPP * 32) : "memory");
+  else __syncthreads();
 }
 
-// cnt = number of live diagonals of the source wavefront (0 when it does not exist)
-__device__ __forceinline__ int32_t k1_guard(const int32_t* row, int k, int lo, int cnt) {
-  return ((unsigned)(k - lo) < (unsigned)cnt) ? row[k] : WNULL;
+// group barrier + OR-reduction of a predicate
+template <int WPP>
+__device__ __forceinline__ bool k1_gsync_or(int, bool pred) {
+  if (WPP == 1) { const bool r = __any_sync(FULL, pred); __syncwarp(); return r; }
+  return __syncthreads_or(pred) != 0;
 }
 
 template <int WPP>
@@ -67,15 +78,14 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
   uint2* wp = reinterpret_cast<uint2*>(gs + (size_t)P.rd * P.wcap * 4);
   uint2* wt = wp + P.win_cap;
   int* meta = reinterpret_cast<int*>(wt + P.win_cap);  // [rd][2] lo,hi
-  int* part = meta + 2 * P.rd;                          // [2][WPP][3]
-  int* slot_pair = part + 2 * WPP * 3;                  // [1]
+  int* slot_pair = meta + 2 * P.rd;                     // [0] work index, [1] terminating diagonal
   const int rd = P.rd, wcap = P.wcap;
   unsigned long long cells_acc = 0;
 
   for (;;) {
-    if (g == 0) *reinterpret_cast<volatile int*>(slot_pair) = (int)atomicAdd(P.counter, 1u);
+    if (g == 0) { reinterpret_cast<volatile int*>(slot_pair)[0] = (int)atomicAdd(P.counter, 1u); slot_pair[1] = INT_MAX; }
     k1_gsync<WPP>(group);
-    const uint32_t wi = (uint32_t) * reinterpret_cast<volatile int*>(slot_pair);
+    const uint32_t wi = (uint32_t) reinterpret_cast<volatile int*>(slot_pair)[0];
     if (wi >= P.n) break;
     const uint32_t pi = P.order[wi];
     const DevPair pr = P.pairs[pi];
@@ -87,10 +97,10 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
       for (int i = g; i < nwp; i += G) wp[i] = make_uint2(gp[i], gp[i + 1]);
       for (int i = g; i < nwt; i += G) wt[i] = make_uint2(gt[i], gt[i + 1]);
     }
-    const int kbase = plen + 2;
+    const int kbase = plen + 4;  // element index e = k + kbase >= 3 for every diagonal that is ever read
     k1_gsync<WPP>(group);
 
-    int s = 0, par = 0, res_status = 0, res_score = 0;
+    int s = 0, res_status = 0, res_score = 0;
     for (;; ++s) {
       if (s > P.max_score) { res_status = -7; break; }
       int lo, hi, lox = 1, hix = -1, loi = 1, hii = -1;
@@ -106,92 +116,121 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
           k1_gsync<WPP>(group);
           continue;
         }
-        lo = min(hasx ? lox : INT_MAX, hasi ? loi - 1 : INT_MAX);
-        hi = max(hasx ? hix : INT_MIN, hasi ? hii + 1 : INT_MIN);
+        // computed range, clamped to the diagonals of the matrix (cells outside are always null)
+        lo = max(min(hasx ? lox : INT_MAX, hasi ? loi - 1 : INT_MAX), -plen);
+        hi = min(max(hasx ? hix : INT_MIN, hasi ? hii + 1 : INT_MIN), tlen);
       }
-      // interior: every read of every source is in range (unguarded fast path)
-      const int ilo = max(lox, loi + 1), ihi = min(hix, hii - 1);
+      if (g == 0) { meta[2 * (s % rd)] = lo; meta[2 * (s % rd) + 1] = hi; cells_acc += (unsigned long long)(hi - lo + 1); }
+      const int ilo = max(max(lox, loi + 1), lo), ihi = min(min(hix, hii - 1), hi);  // every read in range, every cell active
       const int cntx = max(hix - lox + 1, 0), cnti = max(hii - loi + 1, 0);
-      const int32_t* rowX = ring + (size_t)((sx >= 0 ? sx : 0) % rd) * wcap + kbase;
-      const int32_t* rowI = ring + (size_t)((si >= 0 ? si : 0) % rd) * wcap + kbase;
-      int32_t* rowO = ring + (size_t)(s % rd) * wcap + kbase;
-      int term_k = INT_MAX, nn_lo = INT_MAX, nn_hi = INT_MIN;
-      if (g == 0) cells_acc += (unsigned long long)(hi - lo + 1);
+      const int32_t* rowX = ring + (size_t)((sx >= 0 ? sx : 0) % rd) * wcap;
+      const int32_t* rowI = ring + (size_t)((si >= 0 ? si : 0) % rd) * wcap;
+      int32_t* rowO = ring + (size_t)(s % rd) * wcap;
+      int term_k = INT_MAX;
+      const int g_lo = (lo + kbase) >> 2, g_hi = (hi + kbase) >> 2;
 
-      for (int kb = lo + gw * 32; kb <= hi; kb += G) {
-        const int k = kb + lane;
-        const bool act = k <= hi;
-        int32_t cell = WNULL;
+      for (int gb = g_lo + gw * 32; gb <= g_hi; gb += G) {
+        const int gi = gb + lane;
+        const bool gact = gi <= g_hi;
+        const int e0 = gi << 2, k0 = e0 - kbase;
+        int32_t cell[4];
         if (s == 0) {
-          if (act) cell = (max(k, 0) << 16) | (k + K1_K0BIAS);
-        } else {
-          int32_t a, b, c;
-          if (kb >= ilo && kb + 31 <= ihi) {
-            a = rowX[k]; b = rowI[k - 1]; c = rowI[k + 1];
-          } else {
-            a = k1_guard(rowX, k, lox, cntx);
-            b = k1_guard(rowI, k - 1, loi, cnti);
-            c = k1_guard(rowI, k + 1, loi, cnti);
-          }
-          const int32_t mis = a + (K1_ONE | K1_TX), ins = b + K1_ONE, del = c | K1_TD;
-          cell = max(max(mis, del), ins) & ~K1_TMASK;
-          if (!act) cell = WNULL;
-        }
-        int off = cell >> 16;
-        if ((unsigned)off > (unsigned)tlen || (unsigned)(off - k) > (unsigned)plen) cell = WNULL;
-        bool pending = false;
-        if (cell >= 0) {  // extend along matches: two private windows, then warp-cooperative
-          const int v = off - k;
-          uint32_t xw = window8(wp, v) ^ window8(wt, off);
-          if (xw) off += lead_eq(xw);
-          else {
-            off += 8;
-            xw = window8(wp, v + 8) ^ window8(wt, off);
-            if (xw) off += lead_eq(xw);
-            else { off += 8; pending = true; }
-          }
-        }
-        unsigned pm = __ballot_sync(FULL, pending);
-        while (pm) {
-          const int src = __ffs((int)pm) - 1;
-          pm &= pm - 1;
-          const int ko = __shfl_sync(FULL, k, src), ho = __shfl_sync(FULL, off, src);
-          const int adv = coop_extend(wp, wt, plen, tlen, ko, ho, lane);
-          if (lane == src) off += adv;
-        }
-        if (cell >= 0) {
-          cell = (cell & 0xFFFF) | (off << 16);
-          const int v = off - k;
-          if ((off >= tlen && plen - v <= pr.pef) || (v >= plen && tlen - off <= pr.tef)) term_k = min(term_k, k);
-          nn_lo = min(nn_lo, k);
-          nn_hi = max(nn_hi, k);
-        }
-        if (act) rowO[k] = cell;
-      }
-      term_k = warp_min(term_k);
-      nn_lo = warp_min(nn_lo);
-      nn_hi = warp_max(nn_hi);
-      if (WPP > 1) {
-        int* pp = part + par * WPP * 3;
-        if (lane == 0) { pp[gw * 3] = term_k; pp[gw * 3 + 1] = nn_lo; pp[gw * 3 + 2] = nn_hi; }
-        k1_gsync<WPP>(group);
 #pragma unroll
-        for (int w = 0; w < WPP; ++w) {
-          term_k = min(term_k, pp[w * 3]);
-          nn_lo = min(nn_lo, pp[w * 3 + 1]);
-          nn_hi = max(nn_hi, pp[w * 3 + 2]);
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            cell[j] = (k >= lo && k <= hi) ? ((max(k, 0) << 16) | (k + K1_K0BIAS)) : WNULL;
+          }
+        } else {
+          int4 a = make_int4(WNULL, WNULL, WNULL, WNULL), b = a;
+          int32_t bl = WNULL, br = WNULL;
+          if (gact) {
+            a = *reinterpret_cast<const int4*>(rowX + e0);
+            b = *reinterpret_cast<const int4*>(rowI + e0);
+            bl = rowI[e0 - 1];
+            br = rowI[e0 + 4];
+          }
+          int32_t av[4] = {a.x, a.y, a.z, a.w};
+          int32_t bm[4] = {bl, b.x, b.y, b.z};  // k-1
+          int32_t bp[4] = {b.y, b.z, b.w, br};  // k+1
+          const int kA = (gb << 2) - kbase;
+          if (!(kA >= ilo && kA + 127 <= ihi)) {  // boundary chunk: check each read against its source range
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k = k0 + j;
+              const bool act = k >= lo && k <= hi;
+              av[j] = (act && (unsigned)(k - lox) < (unsigned)cntx) ? av[j] : WNULL;
+              bm[j] = (act && (unsigned)(k - 1 - loi) < (unsigned)cnti) ? bm[j] : WNULL;
+              bp[j] = (act && (unsigned)(k + 1 - loi) < (unsigned)cnti) ? bp[j] : WNULL;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int32_t mis = av[j] + (K1_ONE | K1_TX), ins = bm[j] + K1_ONE, del = bp[j] | K1_TD;
+            cell[j] = max(max(mis, del), ins) & ~K1_TMASK;
+          }
         }
-        par ^= 1;
-        if (g == 0) { meta[2 * (s % rd)] = nn_lo <= nn_hi ? nn_lo : 1; meta[2 * (s % rd) + 1] = nn_lo <= nn_hi ? nn_hi : -1; }
-        if (min(P.x, P.ip) < 2 || term_k != INT_MAX) k1_gsync<WPP>(group);
-      } else {
-        if (lane == 0) { meta[2 * (s % rd)] = nn_lo <= nn_hi ? nn_lo : 1; meta[2 * (s % rd) + 1] = nn_lo <= nn_hi ? nn_hi : -1; }
-        __syncwarp();
+        // bounds + first 8-base window of the four cells (independent chains)
+        uint32_t xw[4];
+        int off[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + j;
+          off[j] = cell[j] >> 16;
+          if ((unsigned)off[j] > (unsigned)tlen || (unsigned)(off[j] - k) > (unsigned)plen) { cell[j] = WNULL; off[j] = -1; }
+          const bool valid = off[j] >= 0;
+          xw[j] = window8(wp, valid ? off[j] - k : 0) ^ window8(wt, valid ? off[j] : 0);
+        }
+        bool more = false, edge = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool valid = off[j] >= 0;
+          if (valid) off[j] += xw[j] ? lead_eq(xw[j]) : 8;
+          more = more || (valid && xw[j] == 0u);
+        }
+        if (__any_sync(FULL, more)) {  // rare: a run longer than 8 bases (the true diagonal)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            bool pending = false;
+            if (off[j] >= 0 && xw[j] == 0u) {
+              const uint32_t x2 = window8(wp, off[j] - k) ^ window8(wt, off[j]);
+              if (x2) off[j] += lead_eq(x2);
+              else { off[j] += 8; pending = true; }
+            }
+            unsigned pm = __ballot_sync(FULL, pending);
+            while (pm) {
+              const int src = __ffs((int)pm) - 1;
+              pm &= pm - 1;
+              const int ko = __shfl_sync(FULL, k, src), ho = __shfl_sync(FULL, off[j], src);
+              const int adv = coop_extend(wp, wt, plen, tlen, ko, ho, lane);
+              if (lane == src) off[j] += adv;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (off[j] >= 0) cell[j] = (cell[j] & 0xFFFF) | (off[j] << 16);
+          edge = edge || off[j] >= tlen || off[j] - (k0 + j) >= plen;
+        }
+        if (edge) {  // a cell touches the end of a sequence: full ends-free termination test (rare)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j, v = off[j] - k;
+            if (off[j] >= 0 && ((off[j] >= tlen && plen - v <= pr.pef) || (v >= plen && tlen - off[j] <= pr.tef)))
+              term_k = min(term_k, k);
+          }
+        }
+        if (gact) *reinterpret_cast<int4*>(rowO + e0) = make_int4(cell[0], cell[1], cell[2], cell[3]);
       }
-      if (term_k != INT_MAX) {
-        const int32_t cell = rowO[term_k];
-        const int off = cell >> 16, k0 = (cell & 0x3FFF) - K1_K0BIAS;
-        const int aligned = off + (off - term_k) - abs(k0);
+      // ---- one barrier per score: rows complete + did any diagonal terminate ----
+      term_k = warp_min(term_k);
+      if (term_k != INT_MAX && lane == 0) atomicMin(slot_pair + 1, term_k);
+      if (k1_gsync_or<WPP>(group, term_k != INT_MAX)) {
+        if (WPP > 1) k1_gsync<WPP>(group);  // the atomicMin of every warp is visible
+        const int tk = reinterpret_cast<volatile int*>(slot_pair)[1];
+        const int32_t cellv = rowO[tk + kbase];
+        const int offv = cellv >> 16, k0v = (cellv & 0x3FFF) - K1_K0BIAS;
+        const int aligned = offv + (offv - tk) - abs(k0v);
         res_score = (P.match == 0) ? -s : ((-P.match) * aligned - s) / 2;
         break;
       }

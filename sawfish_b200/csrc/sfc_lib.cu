@@ -162,6 +162,8 @@ constexpr int kNumK1Classes = 4;
 template <int WPP>
 int launch_k1(sfc_ctx* c, const K1Params& P, int groups_per_block, int grid, size_t smem) {
   CU(cudaFuncSetAttribute(k1_score<WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // ask for the full shared-memory carveout: occupancy of this kernel is set by shared memory, not by L1
+  CU(cudaFuncSetAttribute(k1_score<WPP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   k1_score<WPP><<<grid, groups_per_block * WPP * 32, smem, c->stream>>>(P);
   CU(cudaGetLastError());
   return 0;
@@ -336,7 +338,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
   std::vector<uint32_t> k2_small, k2_large;
   for (size_t i = 0; i < n; ++i) {
     const DevPair& d = c->h_pairs[i];
-    const long long W = (long long)d.plen + d.tlen + 5;
+    const long long W = (long long)d.plen + d.tlen + 12;  // ring row: diagonals -plen-1..tlen+1 plus vector-group slack
     bool k1 = (a.metric == 0) && !want_cigar && d.plen <= K1_MAX_LEN && d.tlen <= K1_MAX_LEN && d.pbf <= K1_MAX_FREE &&
               d.tbf <= K1_MAX_FREE && lookL <= 32;
     if (k1) {
@@ -344,7 +346,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       for (int j = 0; j < kNumK1Classes; ++j) if (W <= kK1Classes[j].wcap) { cls = j; break; }
       if (cls >= 0) { k1_lists[cls].push_back((uint32_t)i); continue; }
     }
-    if (W <= 4096) k2_small.push_back((uint32_t)i); else k2_large.push_back((uint32_t)i);
+    if (W <= 4096 + 7) k2_small.push_back((uint32_t)i); else k2_large.push_back((uint32_t)i);
   }
   auto sort_heavy_first = [&](std::vector<uint32_t>& v) {
     std::stable_sort(v.begin(), v.end(), [&](uint32_t x, uint32_t y) {
