@@ -77,6 +77,9 @@ typedef struct {
   char* ex[NCOMP];
   int32_t* nullrow;
   uint8_t** bt;
+  uint8_t** bt_chunks; /* choice bytes live in 4 MiB arena chunks (one malloc per chunk, not per score) */
+  int n_bt_chunks, cap_bt_chunks;
+  size_t bt_chunk_used, bt_chunk_size;
   int* btlo;
   int S_cap;
   size_t mem_used, mem_cap;
@@ -90,6 +93,27 @@ static void* xalloc(wfa_t* w, size_t n) {
   if (!p) { w->oom = 1; return NULL; }
   w->mem_used += n;
   return p;
+}
+
+static uint8_t* bt_alloc(wfa_t* w, size_t n) {
+  if (w->n_bt_chunks == 0 || w->bt_chunk_used + n > w->bt_chunk_size) {
+    const size_t sz = n > ((size_t)4 << 20) ? n : ((size_t)4 << 20);
+    if (w->n_bt_chunks == w->cap_bt_chunks) {
+      const int nc = w->cap_bt_chunks ? 2 * w->cap_bt_chunks : 16;
+      uint8_t** p = (uint8_t**)realloc(w->bt_chunks, sizeof(uint8_t*) * (size_t)nc);
+      if (!p) { w->oom = 1; return NULL; }
+      w->bt_chunks = p;
+      w->cap_bt_chunks = nc;
+    }
+    uint8_t* c = (uint8_t*)xalloc(w, sz);
+    if (!c) return NULL;
+    w->bt_chunks[w->n_bt_chunks++] = c;
+    w->bt_chunk_used = 0;
+    w->bt_chunk_size = sz;
+  }
+  uint8_t* r = w->bt_chunks[w->n_bt_chunks - 1] + w->bt_chunk_used;
+  w->bt_chunk_used += n;
+  return r;
 }
 
 static inline int slot_of(const wfa_t* w, int c, int s) {
@@ -190,7 +214,7 @@ static int compute(wfa_t* w, int s) {
     if (!out[c]) return -3;
   }
   const int width = hi - lo + 1;
-  uint8_t* bt = (uint8_t*)xalloc(w, (size_t)width);
+  uint8_t* bt = bt_alloc(w, (size_t)width);
   if (!bt) return -3;
   w->bt[s] = bt;
   w->btlo[s] = lo;
@@ -200,52 +224,50 @@ static int compute(wfa_t* w, int s) {
   if (!aff) {
     const int32_t *mx = MX.row, *mg = MO1.row;
     int32_t* om = out[C_M];
+    uint8_t* __restrict__ btp = bt - lo;
+#pragma omp simd
     for (int k = lo; k <= hi; ++k) {
       const int32_t ins = mg[k - 1] + 1, del = mg[k + 1], mis = mx[k] + 1;
-      int32_t best = ins;
-      uint8_t sel = SEL_I1;
-      if (del >= best) { best = del; sel = SEL_D1; }
-      if (mis >= best) { best = mis; sel = SEL_X; }
+      int32_t best = ins, sel = SEL_I1;
+      sel = del >= best ? SEL_D1 : sel; best = del >= best ? del : best;
+      sel = mis >= best ? SEL_X : sel;  best = mis >= best ? mis : best;
       const uint32_t h = (uint32_t)best, v = (uint32_t)(best - k);
-      if (h > (uint32_t)tlen || v > (uint32_t)plen) best = ONULL;
+      best = (h > (uint32_t)tlen || v > (uint32_t)plen) ? ONULL : best;
       om[k] = best;
-      bt[k - lo] = sel;
+      btp[k] = (uint8_t)sel;
     }
     trim(w, C_M, s, om, lo, hi);
     return 0;
   }
-  const int32_t *mx = MX.row, *mo1 = MO1.row, *mo2 = MO2.row;
-  const int32_t *i1e = I1E.row, *d1e = D1E.row, *i2e = I2E.row, *d2e = D2E.row;
-  int32_t *om = out[C_M], *oi1 = out[C_I1], *od1 = out[C_D1], *oi2 = out[C_I2], *od2 = out[C_D2];
+  const int32_t *__restrict__ mx = MX.row, *__restrict__ mo1 = MO1.row, *__restrict__ mo2 = MO2.row;
+  const int32_t *__restrict__ i1e = I1E.row, *__restrict__ d1e = D1E.row, *__restrict__ i2e = I2E.row, *__restrict__ d2e = D2E.row;
+  int32_t *__restrict__ om = out[C_M], *__restrict__ oi1 = out[C_I1], *__restrict__ od1 = out[C_D1], *__restrict__ oi2 = out[C_I2], *__restrict__ od2 = out[C_D2];
+  /* branch-free body so the compiler can vectorise it (WFA2-lib's own kernels are auto-vectorised the same way) */
+  uint8_t* __restrict__ btp = bt - lo;
+#pragma omp simd
   for (int k = lo; k <= hi; ++k) {
-    uint8_t c = 0;
     const int32_t i1o_v = mo1[k - 1], i1e_v = i1e[k - 1];
-    int32_t ins1 = MAXI(i1o_v, i1e_v) + 1;
-    if (i1e_v >= i1o_v) c |= BIT_I1E;
     const int32_t i2o_v = mo2[k - 1], i2e_v = i2e[k - 1];
-    int32_t ins2 = MAXI(i2o_v, i2e_v) + 1;
-    if (i2e_v >= i2o_v) c |= BIT_I2E;
     const int32_t d1o_v = mo1[k + 1], d1e_v = d1e[k + 1];
-    int32_t del1 = MAXI(d1o_v, d1e_v);
-    if (d1e_v >= d1o_v) c |= BIT_D1E;
     const int32_t d2o_v = mo2[k + 1], d2e_v = d2e[k + 1];
-    int32_t del2 = MAXI(d2o_v, d2e_v);
-    if (d2e_v >= d2o_v) c |= BIT_D2E;
+    const int32_t ins1 = MAXI(i1o_v, i1e_v) + 1, ins2 = MAXI(i2o_v, i2e_v) + 1;
+    const int32_t del1 = MAXI(d1o_v, d1e_v), del2 = MAXI(d2o_v, d2e_v);
     const int32_t mis = mx[k] + 1;
-    int32_t best = ins1;
-    uint8_t sel = SEL_I1;
-    if (ins2 >= best) { best = ins2; sel = SEL_I2; }
-    if (del1 >= best) { best = del1; sel = SEL_D1; }
-    if (del2 >= best) { best = del2; sel = SEL_D2; }
-    if (mis >= best) { best = mis; sel = SEL_X; }
+    int32_t c = (i1e_v >= i1o_v ? BIT_I1E : 0) | (i2e_v >= i2o_v ? BIT_I2E : 0) | (d1e_v >= d1o_v ? BIT_D1E : 0) |
+                (d2e_v >= d2o_v ? BIT_D2E : 0);
+    int32_t best = ins1, sel = SEL_I1;
+    sel = ins2 >= best ? SEL_I2 : sel; best = ins2 >= best ? ins2 : best;
+    sel = del1 >= best ? SEL_D1 : sel; best = del1 >= best ? del1 : best;
+    sel = del2 >= best ? SEL_D2 : sel; best = del2 >= best ? del2 : best;
+    sel = mis >= best ? SEL_X : sel;   best = mis >= best ? mis : best;
     const uint32_t h = (uint32_t)best, v = (uint32_t)(best - k);
-    if (h > (uint32_t)tlen || v > (uint32_t)plen) best = ONULL;
+    best = (h > (uint32_t)tlen || v > (uint32_t)plen) ? ONULL : best;
     om[k] = best;
     oi1[k] = ins1 < 0 ? ONULL : ins1;
     oi2[k] = ins2 < 0 ? ONULL : ins2;
     od1[k] = del1 < 0 ? ONULL : del1;
     od2[k] = del2 < 0 ? ONULL : del2;
-    bt[k - lo] = (uint8_t)(c | sel);
+    btp[k] = (uint8_t)(c | sel);
   }
   trim(w, C_M, s, om, lo, hi);
   trim(w, C_I1, s, oi1, lo, hi);
@@ -477,10 +499,9 @@ static void wfa_free(wfa_t* w) {
     free(w->hi[c]);
     free(w->ex[c]);
   }
-  if (w->bt) {
-    for (int s = 0; s <= w->S_cap; ++s) free(w->bt[s]);
-    free(w->bt);
-  }
+  for (int i = 0; i < w->n_bt_chunks; ++i) free(w->bt_chunks[i]);
+  free(w->bt_chunks);
+  free(w->bt);
   free(w->btlo);
   free(w->nullrow);
   free(w->p);

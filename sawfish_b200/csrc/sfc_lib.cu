@@ -156,15 +156,19 @@ void init_lut_host(uint8_t* lut) {
 
 // ---- K1 size classes (shared-memory ring) ----
 struct K1Class { int wcap; int wpp; };
-const K1Class kK1Classes[] = {{640, 2}, {1152, 4}, {2304, 8}, {4352, 8}};
-constexpr int kNumK1Classes = 4;
+// finer classes = less shared memory per pair = more pairs resident per SM; classes run concurrently
+const K1Class kK1Classes[] = {{256, 1}, {384, 2}, {512, 2}, {640, 2}, {768, 4}, {896, 4}, {1024, 4}, {1152, 4},
+                              {1536, 8}, {2304, 8}, {3328, 8}, {4352, 8}};
+constexpr int kNumK1Classes = 12;
 
 template <int WPP>
-int launch_k1(sfc_ctx* c, const K1Params& P, int groups_per_block, int grid, size_t smem) {
-  CU(cudaFuncSetAttribute(k1_score<WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+int launch_k1(sfc_ctx* c, const K1Params& P, int groups_per_block, int grid, size_t smem, cudaStream_t st) {
+  static thread_local size_t attr_smem = 0;  // the attribute must cover every concurrently launched class
+  attr_smem = std::max(attr_smem, smem);
+  CU(cudaFuncSetAttribute(k1_score<WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr_smem));
   // ask for the full shared-memory carveout: occupancy of this kernel is set by shared memory, not by L1
   CU(cudaFuncSetAttribute(k1_score<WPP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  k1_score<WPP><<<grid, groups_per_block * WPP * 32, smem, c->stream>>>(P);
+  k1_score<WPP><<<grid, groups_per_block * WPP * 32, smem, st>>>(P);
   CU(cudaGetLastError());
   return 0;
 }
@@ -315,7 +319,7 @@ extern "C" int sfc_batch_upload(sfc_ctx* c, const uint8_t* arena, size_t arena_l
 }
 
 // ============================================================================ run
-// d_misc layout (uint32 words): [0] K1 work counter, [2..3] cells (u64), [4..5] pool_used (u64),
+// d_misc layout (uint32 words): [2..3] cells (u64), [4..5] pool_used (u64), [16..27] K1 class work counters,
 // [8] K2 work counter, [32] bad-symbol flag.
 extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_cigar) {
   if (!c) return SFC_ERR_INVALID;
@@ -378,7 +382,10 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
   CU(cudaMemsetAsync(misc + 40, 0, 32, c->stream));  // optional phase timers
   c->stats.h2d_bytes += n * 4;
 
-  // ---- K1 launches ----
+  // ---- K1 launches: one per size class, concurrently on the job streams (fork / join with events) ----
+  CU(cudaMemsetAsync(misc + 16, 0, 64, c->stream));  // per-class work counters
+  CU(cudaEventRecord(c->job_ev[6], c->stream));
+  int k1_launched = 0;
   for (int j = 0; j < kNumK1Classes; ++j) {
     const size_t cnt = k1_begin[j + 1] - k1_begin[j];
     if (!cnt) continue;
@@ -414,17 +421,22 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     const int blocks_per_sm = std::max(1, (int)((smem_max + 1024) / (smem + 1024)));
     const size_t need_groups = cnt;
     int grid = (int)std::min<size_t>((need_groups + gpb - 1) / gpb, (size_t)c->sm_count * blocks_per_sm);
-    // each class needs its own work counter value 0: reuse misc[0] sequentially via a memset between launches
-    CU(cudaMemsetAsync(misc, 0, 4, c->stream));
-    P.counter = misc;
+    P.counter = misc + 16 + j;
+    cudaStream_t st = c->job_stream[k1_launched % 6];
+    if (k1_launched < 6) CU(cudaStreamWaitEvent(st, c->job_ev[6], 0));
     switch (wpp) {
-      case 1: rc = launch_k1<1>(c, P, gpb, grid, smem); break;
-      case 2: rc = launch_k1<2>(c, P, gpb, grid, smem); break;
-      case 4: rc = launch_k1<4>(c, P, gpb, grid, smem); break;
-      default: rc = launch_k1<8>(c, P, gpb, grid, smem); break;
+      case 1: rc = launch_k1<1>(c, P, gpb, grid, smem, st); break;
+      case 2: rc = launch_k1<2>(c, P, gpb, grid, smem, st); break;
+      case 4: rc = launch_k1<4>(c, P, gpb, grid, smem, st); break;
+      default: rc = launch_k1<8>(c, P, gpb, grid, smem, st); break;
     }
     if (rc) return rc;
+    ++k1_launched;
     c->stats.launches++;
+  }
+  for (int q = 0; q < std::min(k1_launched, 6); ++q) {
+    CU(cudaEventRecord(c->job_ev[q], c->job_stream[q]));
+    CU(cudaStreamWaitEvent(c->stream, c->job_ev[q], 0));
   }
 
   // ---- K2 launches: jobs by (size class, cluster size), heaviest first, with workspace escalation ----
