@@ -132,41 +132,42 @@ __device__ __forceinline__ int k2_extend_more(const uint2* __restrict__ wp, cons
   return off;
 }
 
-struct K2Rows {  // 32-bit element offsets of the source / destination ring rows of one score step
-  unsigned qMX, qMO1, qMO2, qI1E, qD1E, qI2E, qD2E, wM, wI1, wD1, wI2, wD2;
+template <typename T>
+struct K2Rows {  // row pointers (element 0 of each ring row) of the sources / destinations of one score step
+  const T *pMX, *pMO1, *pMO2, *pI1E, *pD1E, *pI2E, *pD2E;
+  T *oM, *oI1, *oD1, *oI2, *oD2;
 };
 
 // One interior chunk (128 diagonals per warp, 4 per thread): every lane is active and every read of every source
 // lies inside that source's live range, so there are no guards and no predicates — straight-line code.
 template <bool AFF, bool HAS2, typename T>
-__device__ __forceinline__ void k2_fast_chunk(const T* __restrict__ R, T* __restrict__ Wr, unsigned char* __restrict__ btq,
-                                              const K2Rows& q, unsigned e0, int k0, int lane,
+__device__ __forceinline__ void k2_fast_chunk(unsigned char* __restrict__ btq, const K2Rows<T>& q, unsigned e0, int k0, int lane,
                                               const uint2* __restrict__ wp, const uint2* __restrict__ wt,
                                               int plen, int tlen, int pef, int tef, int& term_k) {
   int32_t mx[4], m1[4], best[4];
   uint32_t ch[4];
-  K2Vec<T>::load(R + q.qMX + e0, mx);
-  K2Vec<T>::load(R + q.qMO1 + e0, m1);
+  K2Vec<T>::load(q.pMX + e0, mx);
+  K2Vec<T>::load(q.pMO1 + e0, m1);
   int32_t m1l = __shfl_up_sync(FULL, m1[3], 1), m1r = __shfl_down_sync(FULL, m1[0], 1);
-  if (lane == 0) m1l = R[q.qMO1 + e0 - 1u];
-  if (lane == 31) m1r = R[q.qMO1 + e0 + 4u];
+  if (lane == 0) m1l = q.pMO1[e0 - 1u];
+  if (lane == 31) m1r = q.pMO1[e0 + 4u];
   int32_t ins1[4], del1[4], ins2[4], del2[4];
   if (AFF) {
     int32_t a1[4], d1[4];
-    K2Vec<T>::load(R + q.qI1E + e0, a1);
-    K2Vec<T>::load(R + q.qD1E + e0, d1);
+    K2Vec<T>::load(q.pI1E + e0, a1);
+    K2Vec<T>::load(q.pD1E + e0, d1);
     int32_t a1l = __shfl_up_sync(FULL, a1[3], 1), d1r = __shfl_down_sync(FULL, d1[0], 1);
-    if (lane == 0) a1l = R[q.qI1E + e0 - 1u];
-    if (lane == 31) d1r = R[q.qD1E + e0 + 4u];
+    if (lane == 0) a1l = q.pI1E[e0 - 1u];
+    if (lane == 31) d1r = q.pD1E[e0 + 4u];
     int32_t m2[4], a2[4], d2[4], m2l = WNULL, m2r = WNULL, a2l = WNULL, d2r = WNULL;
     if (HAS2) {
-      K2Vec<T>::load(R + q.qMO2 + e0, m2);
-      K2Vec<T>::load(R + q.qI2E + e0, a2);
-      K2Vec<T>::load(R + q.qD2E + e0, d2);
+      K2Vec<T>::load(q.pMO2 + e0, m2);
+      K2Vec<T>::load(q.pI2E + e0, a2);
+      K2Vec<T>::load(q.pD2E + e0, d2);
       m2l = __shfl_up_sync(FULL, m2[3], 1); m2r = __shfl_down_sync(FULL, m2[0], 1);
       a2l = __shfl_up_sync(FULL, a2[3], 1); d2r = __shfl_down_sync(FULL, d2[0], 1);
-      if (lane == 0) { m2l = R[q.qMO2 + e0 - 1u]; a2l = R[q.qI2E + e0 - 1u]; }
-      if (lane == 31) { m2r = R[q.qMO2 + e0 + 4u]; d2r = R[q.qD2E + e0 + 4u]; }
+      if (lane == 0) { m2l = q.pMO2[e0 - 1u]; a2l = q.pI2E[e0 - 1u]; }
+      if (lane == 31) { m2r = q.pMO2[e0 + 4u]; d2r = q.pD2E[e0 + 4u]; }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -210,9 +211,9 @@ __device__ __forceinline__ void k2_fast_chunk(const T* __restrict__ R, T* __rest
   // choice bytes and I/D rows do not depend on the extension: store them first
   *reinterpret_cast<uint32_t*>(btq + e0) = ch[0] | (ch[1] << 8) | (ch[2] << 16) | (ch[3] << 24);
   if (AFF) {
-    K2Vec<T>::store(Wr + q.wI1 + e0, ins1);
-    K2Vec<T>::store(Wr + q.wD1 + e0, del1);
-    if (HAS2) { K2Vec<T>::store(Wr + q.wI2 + e0, ins2); K2Vec<T>::store(Wr + q.wD2 + e0, del2); }
+    K2Vec<T>::store(q.oI1 + e0, ins1);
+    K2Vec<T>::store(q.oD1 + e0, del1);
+    if (HAS2) { K2Vec<T>::store(q.oI2 + e0, ins2); K2Vec<T>::store(q.oD2 + e0, del2); }
   }
   // bounds + first 8-base window of the four cells (independent chains)
   uint32_t xw[4];
@@ -247,7 +248,7 @@ __device__ __forceinline__ void k2_fast_chunk(const T* __restrict__ R, T* __rest
       }
     }
   }
-  K2Vec<T>::store(Wr + q.wM + e0, best);
+  K2Vec<T>::store(q.oM + e0, best);
 }
 
 template <bool AFF, typename T>
@@ -429,9 +430,10 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
           if (lane == 31 || last_group) right = ok ? (int32_t)R[q + e0 + 4u] : WNULL;  // lane+1 holds nothing useful
         }
       };
-      K2Rows rows;
-      rows.qMX = qMX; rows.qMO1 = qMO1; rows.qMO2 = qMO2; rows.qI1E = qI1E; rows.qD1E = qD1E; rows.qI2E = qI2E; rows.qD2E = qD2E;
-      rows.wM = wM; rows.wI1 = wI1; rows.wD1 = wD1; rows.wI2 = wI2; rows.wD2 = wD2;
+      K2Rows<T> rows;
+      rows.pMX = R + qMX; rows.pMO1 = R + qMO1; rows.pMO2 = R + qMO2; rows.pI1E = R + qI1E; rows.pD1E = R + qD1E;
+      rows.pI2E = R + qI2E; rows.pD2E = R + qD2E;
+      rows.oM = rings + wM; rows.oI1 = rings + wI1; rows.oD1 = rings + wD1; rows.oI2 = rings + wI2; rows.oD2 = rings + wD2;
       unsigned char* btq = btrow - ((size_t)g_lo << 2);  // indexed by the element offset e = k + kbase
       const int flo = max(ilo, lo), fhi = min(ihi, hi);
       for (int gb = g_lo + (crank * NW + warp) * 32; gb <= g_hi; gb += C * NW * 32) {
@@ -440,8 +442,8 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
         const unsigned e0 = (unsigned)g << 2;
         const int k0 = (int)e0 - kbase;
         if (s > 0 && (gb << 2) - kbase >= flo && (gb << 2) - kbase + 127 <= fhi) {  // interior chunk
-          if (has2) k2_fast_chunk<AFF, true, T>(R, rings, btq, rows, e0, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
-          else k2_fast_chunk<AFF, false, T>(R, rings, btq, rows, e0, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+          if (has2) k2_fast_chunk<AFF, true, T>(btq, rows, e0, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+          else k2_fast_chunk<AFF, false, T>(btq, rows, e0, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
           continue;
         }
         int32_t best[4], ins1[4], ins2[4], del1[4], del2[4];

@@ -501,7 +501,8 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       size_t max_fixed = 0, max_win = 0, max_W = 0;
       bool wide = false;
       for (uint32_t pi : list) wide = wide || c->h_pairs[pi].plen > K2_MAX_LEN16 || c->h_pairs[pi].tlen > K2_MAX_LEN16;
-      if (getenv("SFC_K2_WIDE")) wide = true;
+      // int32 rings are slightly faster (no 16-bit pack/unpack); int16 halves the workspace and is used on request
+      if (!getenv("SFC_K2_NARROW")) wide = true;
       pl->wide = wide;
       const size_t esz = wide ? 4 : 2;
       const void* kfn = kernel_of(wide);
