@@ -141,6 +141,24 @@ int sfc_estimate_pair_work(const sfc_penalties*, const sfc_pair* pairs, size_t n
 /* Greedy longest-processing-time assignment of groups to shards (deterministic). shard_of_group: [n_groups]. */
 int sfc_shard_plan(const uint64_t* group_work, size_t n_groups, int n_shards, uint32_t* shard_of_group);
 
+/* ---- one process, several GPUs: the deployment shape of the reference (one rayon pool, no MPI) ----
+ * sfc_multi owns one sfc_ctx + one submitter thread per device.  A batch is split by SV group with sfc_shard_plan
+ * (group_of_pair == NULL: every pair is its own group), each shard gets a compacted copy of just its sequences,
+ * shards run concurrently on their GPUs, and results are gathered on the host in the caller's pair order.
+ * No collective, no peer access: batches are independent (north_star). Replaces the fan-out / mpsc gather of
+ * src/joint_call/joint_call_all_samples.rs:100-149 and src/refine_sv/mod.rs:827-896 for the alignment work. */
+typedef struct sfc_multi sfc_multi;
+int sfc_multi_create(const int* device_ordinals, int n_devices, sfc_multi** out);
+void sfc_multi_destroy(sfc_multi*);
+int sfc_multi_device_count(const sfc_multi*);
+const char* sfc_multi_last_error(const sfc_multi*);
+int sfc_multi_align_batch(sfc_multi*, const sfc_penalties*, const uint8_t* seq_arena, size_t arena_len,
+                          const sfc_pair* pairs, size_t n_pairs, const uint32_t* group_of_pair,
+                          int want_cigar, int32_t* scores, int32_t* status,
+                          uint32_t* ops_rle, size_t ops_cap, uint64_t* ops_off);
+/* kernel milliseconds of the last batch on each device (max = the batch's device time). out: [n_devices] */
+int sfc_multi_last_kernel_ms(const sfc_multi*, double* out);
+
 /* ---- measurement helper: integer-ALU roofline denominator (IADD3/LOP3 issue rate) ---- */
 /* Runs a dependent-chain-free INT32 micro-benchmark and returns giga-ops/s (thread-level ops). */
 int sfc_measure_int_peak(sfc_ctx*, double* gops_per_s, double* sm_clock_mhz_est);

@@ -40,7 +40,8 @@ EXPORTS = [
     "sfc_align_batch", "sfc_batch_upload", "sfc_batch_run", "sfc_batch_download", "sfc_batch_get_stats",
     "sfc_expand_ops", "sfc_translate_cigar", "sfc_translate_rle",
     "sfc_aligner_new_consensus", "sfc_aligner_new_large_indel", "sfc_aligner_free", "sfc_aligner_set_text",
-    "sfc_aligner_align", "sfc_measure_int_peak", "sfc_estimate_pair_work", "sfc_shard_plan",
+    "sfc_aligner_align", "sfc_measure_int_peak", "sfc_estimate_pair_work", "sfc_shard_plan", "sfc_multi_create", "sfc_multi_destroy",
+    "sfc_multi_device_count", "sfc_multi_last_error", "sfc_multi_align_batch", "sfc_multi_last_kernel_ms",
 ]
 
 
@@ -94,6 +95,15 @@ def lib():
     L.sfc_measure_int_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.sfc_estimate_pair_work.argtypes = [C.POINTER(Penalties), vp, C.c_size_t, vp]
     L.sfc_shard_plan.argtypes = [vp, C.c_size_t, C.c_int, vp]
+    L.sfc_multi_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.sfc_multi_destroy.argtypes = [vp]
+    L.sfc_multi_destroy.restype = None
+    L.sfc_multi_device_count.argtypes = [vp]
+    L.sfc_multi_last_error.argtypes = [vp]
+    L.sfc_multi_last_error.restype = C.c_char_p
+    L.sfc_multi_align_batch.argtypes = [vp, C.POINTER(Penalties), u8p, C.c_size_t, vp, C.c_size_t, vp, C.c_int, i32p, i32p, u32p,
+                                        C.c_size_t, u64p]
+    L.sfc_multi_last_kernel_ms.argtypes = [vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("sfc_abi_version", "sfc_device_count"):

@@ -147,3 +147,53 @@ def translate_cigar(wfa_ops: bytes):
     if rc != 0:
         raise SfcError(rc, "sfc_translate_cigar")
     return roff.value, cig[:n.value].copy(), bool(hm.value)
+
+
+class MultiGpuContext:
+    """One process driving several GPUs (the reference's deployment shape): sfc_multi_* of the C ABI."""
+
+    def __init__(self, devices):
+        L = _lib.lib()
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = L.sfc_multi_create(devs, len(devices), C.byref(h))
+        if rc != 0:
+            raise SfcError(rc, "sfc_multi_create failed (B200 devices required; there is no CPU fallback)")
+        self._h, self._L, self.devices = h, L, list(devices)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sfc_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def align_batch(self, pen: Penalties, arena: np.ndarray, pairs: np.ndarray, want_cigar: bool, group_of_pair=None):
+        n = len(pairs)
+        scores = np.empty(n, np.int32)
+        status = np.empty(n, np.int32)
+        ops_off = np.zeros(n + 1, np.uint64)
+        grp = None if group_of_pair is None else np.ascontiguousarray(group_of_pair, np.uint32)
+        cap = max(1 << 16, 64 * n) if want_cigar else 0
+        while True:
+            ops = np.empty(max(cap, 1), np.uint32)
+            rc = self._L.sfc_multi_align_batch(self._h, C.byref(pen), arena.ctypes.data, arena.size, pairs.ctypes.data, n,
+                                               None if grp is None else grp.ctypes.data, int(want_cigar), scores.ctypes.data,
+                                               status.ctypes.data, ops.ctypes.data if want_cigar else None, cap,
+                                               ops_off.ctypes.data if want_cigar else None)
+            if rc == -4 and want_cigar:
+                cap = int(ops_off[n]) + 16
+                continue
+            if rc != 0:
+                raise SfcError(rc, (self._L.sfc_multi_last_error(self._h) or b"").decode())
+            break
+        return scores, status, (ops[:int(ops_off[n])] if want_cigar else None), (ops_off if want_cigar else None)
+
+    def last_kernel_ms(self):
+        out = np.zeros(len(self.devices), np.float64)
+        self._L.sfc_multi_last_kernel_ms(self._h, out.ctypes.data)
+        return out

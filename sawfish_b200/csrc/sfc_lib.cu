@@ -15,6 +15,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sfc_device.cuh"
@@ -946,6 +947,151 @@ extern "C" int sfc_shard_plan(const uint64_t* group_work, size_t n_groups, int n
     for (int s = 1; s < n_shards; ++s) if (load[s] < load[best]) best = s;
     shard_of_group[g] = (uint32_t)best;
     load[best] += group_work[g] + 1;
+  }
+  return SFC_OK;
+}
+
+// ============================================================================ one process, several GPUs
+struct sfc_multi {
+  std::vector<sfc_ctx*> ctx;
+  std::vector<double> kernel_ms;
+  std::string err;
+};
+
+extern "C" int sfc_multi_create(const int* devs, int n, sfc_multi** out) {
+  if (!devs || n <= 0 || !out) return SFC_ERR_INVALID;
+  *out = nullptr;
+  sfc_multi* m = new (std::nothrow) sfc_multi();
+  if (!m) return SFC_ERR_OOM;
+  for (int i = 0; i < n; ++i) {
+    sfc_ctx* c = nullptr;
+    const int rc = sfc_create(devs[i], &c);
+    if (rc) { sfc_multi_destroy(m); return rc; }
+    m->ctx.push_back(c);
+  }
+  m->kernel_ms.assign((size_t)n, 0.0);
+  *out = m;
+  return SFC_OK;
+}
+
+extern "C" void sfc_multi_destroy(sfc_multi* m) {
+  if (!m) return;
+  for (sfc_ctx* c : m->ctx) sfc_destroy(c);
+  delete m;
+}
+
+extern "C" int sfc_multi_device_count(const sfc_multi* m) { return m ? (int)m->ctx.size() : 0; }
+extern "C" const char* sfc_multi_last_error(const sfc_multi* m) { return m ? m->err.c_str() : "null"; }
+
+extern "C" int sfc_multi_last_kernel_ms(const sfc_multi* m, double* out) {
+  if (!m || !out) return SFC_ERR_INVALID;
+  for (size_t i = 0; i < m->kernel_ms.size(); ++i) out[i] = m->kernel_ms[i];
+  return SFC_OK;
+}
+
+extern "C" int sfc_multi_align_batch(sfc_multi* m, const sfc_penalties* pen, const uint8_t* arena, size_t arena_len,
+                                     const sfc_pair* pairs, size_t n, const uint32_t* group_of_pair, int want_cigar,
+                                     int32_t* scores, int32_t* status, uint32_t* ops_rle, size_t ops_cap, uint64_t* ops_off) {
+  if (!m || !pen || !arena || !pairs || !scores || !status || n == 0) return SFC_ERR_INVALID;
+  if (want_cigar && !ops_off) return SFC_ERR_INVALID;
+  const int nd = (int)m->ctx.size();
+  // ---- plan: LPT over groups by estimated work ----
+  std::vector<uint64_t> work(n);
+  int rc = sfc_estimate_pair_work(pen, pairs, n, work.data());
+  if (rc) { m->err = "invalid penalties"; return rc; }
+  uint32_t n_groups = 0;
+  for (size_t i = 0; i < n; ++i) n_groups = std::max(n_groups, (group_of_pair ? group_of_pair[i] : (uint32_t)i) + 1);
+  std::vector<uint64_t> gwork(n_groups, 0);
+  for (size_t i = 0; i < n; ++i) gwork[group_of_pair ? group_of_pair[i] : (uint32_t)i] += work[i];
+  std::vector<uint32_t> shard_of_group(n_groups);
+  if ((rc = sfc_shard_plan(gwork.data(), n_groups, nd, shard_of_group.data()))) return rc;
+  // ---- per shard: pair list + compacted arena ----
+  struct Shard {
+    std::vector<uint32_t> idx;
+    std::vector<sfc_pair> pairs;
+    std::vector<uint8_t> arena;
+    std::vector<int32_t> scores, status;
+    std::vector<uint32_t> ops;
+    std::vector<uint64_t> ops_off;
+    int rc = 0;
+  };
+  std::vector<Shard> sh((size_t)nd);
+  for (size_t i = 0; i < n; ++i) {
+    const sfc_pair& p = pairs[i];
+    if (p.pattern_off + p.pattern_len > arena_len || p.text_off + p.text_len > arena_len) { m->err = "sequence outside arena"; return SFC_ERR_INVALID; }
+    sh[shard_of_group[group_of_pair ? group_of_pair[i] : (uint32_t)i]].idx.push_back((uint32_t)i);
+  }
+  for (Shard& s : sh) {
+    s.pairs.reserve(s.idx.size());
+    uint64_t last_t_off = ~0ull, last_t_new = 0;  // consecutive pairs usually share their text (one read flank, several alleles)
+    uint32_t last_t_len = 0;
+    for (uint32_t i : s.idx) {
+      sfc_pair q = pairs[i];
+      if (q.text_off == last_t_off && q.text_len == last_t_len) q.text_off = last_t_new;
+      else {
+        last_t_off = q.text_off; last_t_len = q.text_len; last_t_new = s.arena.size();
+        s.arena.insert(s.arena.end(), arena + q.text_off, arena + q.text_off + q.text_len);
+        q.text_off = last_t_new;
+      }
+      const uint64_t pn = s.arena.size();
+      s.arena.insert(s.arena.end(), arena + q.pattern_off, arena + q.pattern_off + q.pattern_len);
+      q.pattern_off = pn;
+      s.pairs.push_back(q);
+    }
+    s.scores.resize(s.idx.size());
+    s.status.resize(s.idx.size());
+    if (want_cigar) { s.ops_off.resize(s.idx.size() + 1); s.ops.resize(std::max<size_t>(s.idx.size() * 64, 1 << 16)); }
+  }
+  // ---- one submitter thread per GPU ----
+  std::vector<std::thread> th;
+  for (int d = 0; d < nd; ++d) {
+    th.emplace_back([&, d]() {
+      Shard& s = sh[(size_t)d];
+      m->kernel_ms[(size_t)d] = 0.0;
+      if (s.idx.empty()) return;
+      sfc_ctx* c = m->ctx[(size_t)d];
+      s.rc = sfc_batch_upload(c, s.arena.data(), s.arena.size(), s.pairs.data(), s.pairs.size());
+      if (!s.rc) s.rc = sfc_batch_run(c, pen, want_cigar);
+      if (!s.rc) {
+        s.rc = sfc_batch_download(c, s.scores.data(), s.status.data(), want_cigar ? s.ops.data() : nullptr, s.ops.size(),
+                                  want_cigar ? s.ops_off.data() : nullptr);
+        if (s.rc == SFC_ERR_CAPACITY) {
+          s.ops.resize((size_t)s.ops_off[s.idx.size()] + 16);
+          s.rc = sfc_batch_download(c, s.scores.data(), s.status.data(), s.ops.data(), s.ops.size(), s.ops_off.data());
+        }
+      }
+      sfc_batch_stats st;
+      if (!sfc_batch_get_stats(c, &st)) m->kernel_ms[(size_t)d] = st.kernel_ms;
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int d = 0; d < nd; ++d) {
+    if (sh[(size_t)d].rc) { m->err = std::string("device ") + std::to_string(d) + ": " + sfc_last_error(m->ctx[(size_t)d]); return sh[(size_t)d].rc; }
+  }
+  // ---- host-side gather in the caller's pair order ----
+  std::vector<uint32_t> where(n);  // position inside its shard
+  std::vector<uint8_t> shard_of_pair(n);
+  for (int d = 0; d < nd; ++d)
+    for (size_t j = 0; j < sh[(size_t)d].idx.size(); ++j) {
+      const uint32_t i = sh[(size_t)d].idx[j];
+      where[i] = (uint32_t)j; shard_of_pair[i] = (uint8_t)d;
+      scores[i] = sh[(size_t)d].scores[j];
+      status[i] = sh[(size_t)d].status[j];
+    }
+  if (want_cigar) {
+    uint64_t acc = 0;
+    for (size_t i = 0; i < n; ++i) {
+      const Shard& s = sh[shard_of_pair[i]];
+      ops_off[i] = acc;
+      acc += s.ops_off[where[i] + 1] - s.ops_off[where[i]];
+    }
+    ops_off[n] = acc;
+    if (acc > ops_cap || (!ops_rle && acc)) { m->err = "ops buffer too small"; return SFC_ERR_CAPACITY; }
+    for (size_t i = 0; i < n; ++i) {
+      const Shard& s = sh[shard_of_pair[i]];
+      const uint64_t b = s.ops_off[where[i]], e = s.ops_off[where[i] + 1];
+      if (e > b) memcpy(ops_rle + ops_off[i], s.ops.data() + b, (size_t)(e - b) * 4);
+    }
   }
   return SFC_OK;
 }

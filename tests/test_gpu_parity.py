@@ -125,3 +125,27 @@ def test_invalid_inputs_fail_loudly(ctx):
         ctx.align_batch(CONSENSUS_PENALTIES, bad_sym, ok, False)
     s, st, _, _ = ctx.align_batch(CONSENSUS_PENALTIES, arena, ok, False)
     assert st[0] == 0
+
+
+def test_single_process_multi_gpu_sharding(ctx):
+    """sfc_multi_*: shard by SV group over every visible GPU, gather on the host; identical to one-GPU results."""
+    from sawfish_b200 import _lib, synth
+    from sawfish_b200.batch import MultiGpuContext
+    lin, aff = _pens()
+    ndev = _lib.lib().sfc_device_count()
+    devices = list(range(min(ndev, 8)))
+    multi = MultiGpuContext(devices)
+    try:
+        arena, pairs, _ = synth.config2b_score_sv_flanks(4000, seed=21)
+        groups = np.arange(len(pairs), dtype=np.uint32) // 8
+        s1, st1, _, _ = ctx.align_batch(lin, arena, pairs, False)
+        s2, st2, _, _ = multi.align_batch(lin, arena, pairs, False, group_of_pair=groups)
+        assert (st2 == 0).all() and (s1 == s2).all()
+        arena, pairs = synth.config3_refine_contigs(40, seed=22)
+        s1, st1, o1, f1 = ctx.align_batch(aff, arena, pairs, True)
+        s2, st2, o2, f2 = multi.align_batch(aff, arena, pairs, True)
+        assert (st2 == 0).all() and (s1 == s2).all() and (f1 == f2).all() and (o1 == o2).all()
+        if len(devices) > 1:
+            assert (multi.last_kernel_ms() > 0).all()  # every GPU got work
+    finally:
+        multi.close()
