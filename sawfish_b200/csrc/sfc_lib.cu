@@ -362,7 +362,8 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
   c->h_order.clear();
   size_t k1_begin[kNumK1Classes + 1];
   for (int j = 0; j < kNumK1Classes; ++j) {
-    sort_heavy_first(k1_lists[j]);
+    // no sort inside a K1 class: the classes are narrow in size and the groups pull pairs dynamically, while an
+    // O(n log n) host sort of ~10^5-10^6 pairs per batch shows up in the end-to-end time
     k1_begin[j] = c->h_order.size();
     c->h_order.insert(c->h_order.end(), k1_lists[j].begin(), k1_lists[j].end());
   }
