@@ -140,12 +140,21 @@ struct K2Rows {  // row pointers (element 0 of each ring row) of the sources / d
 
 // One interior chunk (128 diagonals per warp, 4 per thread): every lane is active and every read of every source
 // lies inside that source's live range, so there are no guards and no predicates — straight-line code.
+__device__ __forceinline__ void k2_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <bool AFF, bool HAS2, typename T>
-__device__ __forceinline__ void k2_fast_chunk(unsigned char* __restrict__ btq, const K2Rows<T>& q, unsigned e0, int k0, int lane,
+__device__ __forceinline__ void k2_fast_chunk(unsigned char* __restrict__ btq, const K2Rows<T>& q, unsigned e0, unsigned pf, int k0, int lane,
                                               const uint2* __restrict__ wp, const uint2* __restrict__ wt,
                                               int plen, int tlen, int pef, int tef, int& term_k) {
   int32_t mx[4], m1[4], best[4];
   uint32_t ch[4];
+  if (pf) {  // pull this warp's NEXT chunk of every source row towards L2 while the current chunk is computed
+    k2_prefetch_l2(q.pMX + e0 + pf); k2_prefetch_l2(q.pMO1 + e0 + pf);
+    if (AFF) {
+      k2_prefetch_l2(q.pI1E + e0 + pf); k2_prefetch_l2(q.pD1E + e0 + pf);
+      if (HAS2) { k2_prefetch_l2(q.pMO2 + e0 + pf); k2_prefetch_l2(q.pI2E + e0 + pf); k2_prefetch_l2(q.pD2E + e0 + pf); }
+    }
+  }
   K2Vec<T>::load(q.pMX + e0, mx);
   K2Vec<T>::load(q.pMO1 + e0, m1);
   int32_t m1l = __shfl_up_sync(FULL, m1[3], 1), m1r = __shfl_down_sync(FULL, m1[0], 1);
@@ -442,8 +451,9 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
         const unsigned e0 = (unsigned)g << 2;
         const int k0 = (int)e0 - kbase;
         if (s > 0 && (gb << 2) - kbase >= flo && (gb << 2) - kbase + 127 <= fhi) {  // interior chunk
-          if (has2) k2_fast_chunk<AFF, true, T>(btq, rows, e0, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
-          else k2_fast_chunk<AFF, false, T>(btq, rows, e0, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+          const unsigned pf = (gb + C * NW * 32 + 31 <= g_hi) ? (unsigned)(C * NW * 128) : 0u;  // next chunk of this warp, in elements
+          if (has2) k2_fast_chunk<AFF, true, T>(btq, rows, e0, pf, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+          else k2_fast_chunk<AFF, false, T>(btq, rows, e0, pf, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
           continue;
         }
         int32_t best[4], ins1[4], ins2[4], del1[4], del2[4];
