@@ -215,3 +215,53 @@ def random_pairs(n: int, seed: int, max_len: int = 120, alphabet: bytes = b"ACGT
 def gcups_cells(pairs: np.ndarray) -> int:
     """Full-matrix DP cells sum |p|*|t| (the GCUPS-equivalent numerator of BASELINE.json's metric)."""
     return int((pairs["pattern_len"].astype(np.int64) * pairs["text_len"].astype(np.int64)).sum())
+
+
+def low_complexity_pairs(n: int, seed: int, len_lo: int = 300, len_hi: int = 3000):
+    """Adversarial mid-size pairs where backtrace tie-breaks bite: tandem repeats, homopolymer runs and 2-letter
+    sequences with repeat-unit indels (many co-optimal alignments), N runs, plus random ends-free allowances."""
+    rng = np.random.default_rng(seed)
+    b = _Builder()
+    rows = []
+    for _ in range(n):
+        L = int(rng.integers(len_lo, len_hi + 1))
+        kind = int(rng.integers(0, 4))
+        if kind == 0:    # tandem repeat of a short unit with point noise
+            unit = random_seq(rng, int(rng.integers(1, 7)))
+            t = np.tile(unit, L // len(unit) + 1)[:L].copy()
+            noise = rng.random(L) < 0.01
+            t[noise] = _ACGT[rng.integers(0, 4, int(noise.sum()))]
+        elif kind == 1:  # 2-letter random
+            t = np.frombuffer(b"AC", np.uint8)[rng.integers(0, 2, L)]
+        elif kind == 2:  # homopolymer blocks
+            blocks = []
+            while sum(len(x) for x in blocks) < L:
+                blocks.append(np.full(int(rng.integers(1, 40)), _ACGT[rng.integers(0, 4)], np.uint8))
+            t = np.concatenate(blocks)[:L]
+        else:            # random with an N run (the refine_sv spacer)
+            t = random_seq(rng, L)
+            a = int(rng.integers(0, max(1, L - 100)))
+            t[a:a + 100] = ord("N")
+        p = t.copy()
+        for _ in range(int(rng.integers(1, 4))):   # repeat-scale indels
+            a = int(rng.integers(0, len(p)))
+            n_ev = int(rng.integers(1, 60))
+            if rng.random() < 0.5:
+                p = np.concatenate([p[:a], p[max(0, a - n_ev):a], p[a:]])   # local duplication
+            else:
+                p = np.concatenate([p[:a], p[a + n_ev:]])
+        if len(p) == 0:
+            p = t[:1].copy()
+        p = add_errors(rng, p, 0.003)
+        t_off = b.add_seq(t)
+        p_off = b.add_seq(p)
+        pl, tl = len(p), len(t)
+        if rng.random() < 0.6:
+            c = sawfish_clip(pl, tl)
+            ends = (c, c, c, c)
+        else:
+            ends = (int(rng.integers(0, pl // 2 + 1)), int(rng.integers(0, pl // 2 + 1)), int(rng.integers(0, tl // 2 + 1)),
+                    int(rng.integers(0, tl // 2 + 1)))
+        rows.append((p_off, t_off, pl, tl) + ends + (PAIR_REVERSE if rng.random() < 0.5 else 0,))
+    arena = np.concatenate(b.chunks)
+    return arena, np.array(rows, dtype=PAIR_DTYPE)

@@ -66,6 +66,17 @@ def test_random_small_pairs(ctx, oracle, seed, which):
     compare_with_oracle(oracle, ctx, pen, arena, pairs, want_cigar=which.endswith("cigar"), mode=oracle.MODE_LITERAL)
 
 
+@pytest.mark.parametrize("which", ["linear_score", "linear_cigar", "affine_cigar"])
+def test_low_complexity_mid_size_pairs(ctx, oracle, which):
+    """Tandem repeats / homopolymers / 2-letter sequences / N runs, 300-3000 bp: many co-optimal alignments, so CIGAR
+    parity here exercises every tie-break."""
+    from sawfish_b200 import synth
+    lin, aff = _pens()
+    arena, pairs = synth.low_complexity_pairs(160, seed=len(which) * 7 + 1)
+    pen = lin if which.startswith("linear") else aff
+    compare_with_oracle(oracle, ctx, pen, arena, pairs, want_cigar=which.endswith("cigar"))
+
+
 def test_score_sv_shaped_batch(ctx, oracle):
     # config 2b: 100-500 bp read flank vs ref/alt allele flanks, gap-linear, score only (K1)
     from sawfish_b200 import synth

@@ -153,3 +153,17 @@ def test_batch_driver_matches_single(oracle):
         c = int(pr["pattern_begin_free"])
         r = oracle.wfa_align(oracle.CONSENSUS, p, t, c, c, c, c)
         assert r.score == scores[i] and r.ops == ops[int(off[i]):int(off[i]) + int(stats["n_ops"][i])].tobytes()
+
+
+def test_low_complexity_literal_equals_compact(oracle):
+    from sawfish_b200 import synth
+    arena, pairs = synth.low_complexity_pairs(40, seed=5, len_lo=100, len_hi=500)
+    for pen in (oracle.CONSENSUS, oracle.LARGE_INDEL):
+        for pr in pairs:
+            p = arena[int(pr["pattern_off"]):int(pr["pattern_off"]) + int(pr["pattern_len"])].tobytes()
+            t = arena[int(pr["text_off"]):int(pr["text_off"]) + int(pr["text_len"])].tobytes()
+            if pr["flags"] & 1:
+                p, t = p[::-1], t[::-1]
+            ends = [int(pr[k]) for k in ("pattern_begin_free", "pattern_end_free", "text_begin_free", "text_end_free")]
+            lit = oracle.wfa_align(pen, p, t, *ends, mode=oracle.MODE_LITERAL)   # -4 if the two backtraces disagree
+            assert oracle.dp_min_penalty(pen, p, t, *ends) == lit.stats["wf_score"]
