@@ -164,9 +164,9 @@ constexpr int kNumK1Classes = 12;
 
 template <int WPP>
 int launch_k1(sfc_ctx* c, const K1Params& P, int groups_per_block, int grid, size_t smem, cudaStream_t st) {
-  static thread_local size_t attr_smem = 0;  // the attribute must cover every concurrently launched class
-  attr_smem = std::max(attr_smem, smem);
-  CU(cudaFuncSetAttribute(k1_score<WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr_smem));
+  // always the device maximum: the attribute is per device (shared by every ctx / thread on it), so a smaller value set
+  // by one launch must never undercut another launch in flight
+  CU(cudaFuncSetAttribute(k1_score<WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
   // ask for the full shared-memory carveout: occupancy of this kernel is set by shared memory, not by L1
   CU(cudaFuncSetAttribute(k1_score<WPP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   k1_score<WPP><<<grid, groups_per_block * WPP * 32, smem, st>>>(P);
@@ -498,7 +498,6 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
 
     // size one job's launch: returns grid (in clusters), slab bytes, shared bytes, win_cap
     struct Plan { size_t n_cl, slab, smem, max_fixed; int win_cap; bool wide; };
-    size_t smem_attr = 0;
     auto plan_job = [&](const std::vector<uint32_t>& list, int threads, int C, size_t budget, int divisor, Plan* pl) -> int {
       size_t max_fixed = 0, max_win = 0, max_W = 0;
       bool wide = false;
@@ -522,8 +521,8 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       pl->smem = smem;
       pl->win_cap = (int)((smem - (size_t)nslots * 8 - 64) / 8);
       pl->max_fixed = max_fixed;
-      smem_attr = std::max(smem_attr, smem);  // the attribute must cover every job launched later
-      CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attr));
+      // always the device maximum (see launch_k1): per-device attribute shared by every ctx / thread / job
+      CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
       int occ = 1;
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, threads, smem));
       occ = std::max(1, occ);
@@ -957,7 +956,29 @@ struct sfc_multi {
   std::vector<sfc_ctx*> ctx;
   std::vector<double> kernel_ms;
   std::string err;
+  // per-shard pinned staging (grow-only): compacted arena, pair table, results
+  struct Stage {
+    uint8_t* arena = nullptr; size_t arena_cap = 0;
+    sfc_pair* pairs = nullptr; size_t pairs_cap = 0;
+    int32_t* scores = nullptr; size_t scores_cap = 0;
+    int32_t* status = nullptr; size_t status_cap = 0;
+  };
+  std::vector<Stage> stage;
 };
+
+namespace {
+template <typename T>
+int pinned_reserve(T*& p, size_t& cap, size_t n) {
+  if (n <= cap) return 0;
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+  const size_t want = n + n / 4 + 64;
+  if (cudaMallocHost((void**)&p, want * sizeof(T)) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; return SFC_ERR_OOM; }
+  cap = want;
+  return 0;
+}
+}  // namespace
 
 extern "C" int sfc_multi_create(const int* devs, int n, sfc_multi** out) {
   if (!devs || n <= 0 || !out) return SFC_ERR_INVALID;
@@ -971,12 +992,19 @@ extern "C" int sfc_multi_create(const int* devs, int n, sfc_multi** out) {
     m->ctx.push_back(c);
   }
   m->kernel_ms.assign((size_t)n, 0.0);
+  m->stage.resize((size_t)n);
   *out = m;
   return SFC_OK;
 }
 
 extern "C" void sfc_multi_destroy(sfc_multi* m) {
   if (!m) return;
+  for (auto& st : m->stage) {
+    if (st.arena) cudaFreeHost(st.arena);
+    if (st.pairs) cudaFreeHost(st.pairs);
+    if (st.scores) cudaFreeHost(st.scores);
+    if (st.status) cudaFreeHost(st.status);
+  }
   for (sfc_ctx* c : m->ctx) sfc_destroy(c);
   delete m;
 }
@@ -996,22 +1024,23 @@ extern "C" int sfc_multi_align_batch(sfc_multi* m, const sfc_penalties* pen, con
   if (!m || !pen || !arena || !pairs || !scores || !status || n == 0) return SFC_ERR_INVALID;
   if (want_cigar && !ops_off) return SFC_ERR_INVALID;
   const int nd = (int)m->ctx.size();
-  // ---- plan: LPT over groups by estimated work ----
+  // ---- plan: LPT over groups by estimated work.  Without caller groups, runs of consecutive pairs form the groups
+  // (consecutive pairs share reads / loci in the callers), which keeps the plan O(n) instead of a sort over every pair.
   std::vector<uint64_t> work(n);
   int rc = sfc_estimate_pair_work(pen, pairs, n, work.data());
   if (rc) { m->err = "invalid penalties"; return rc; }
+  const size_t run = group_of_pair ? 1 : std::max<size_t>(1, std::min<size_t>(256, n / ((size_t)nd * 64) + 1));
+  auto group_of = [&](size_t i) -> uint32_t { return group_of_pair ? group_of_pair[i] : (uint32_t)(i / run); };
   uint32_t n_groups = 0;
-  for (size_t i = 0; i < n; ++i) n_groups = std::max(n_groups, (group_of_pair ? group_of_pair[i] : (uint32_t)i) + 1);
+  for (size_t i = 0; i < n; ++i) n_groups = std::max(n_groups, group_of(i) + 1);
   std::vector<uint64_t> gwork(n_groups, 0);
-  for (size_t i = 0; i < n; ++i) gwork[group_of_pair ? group_of_pair[i] : (uint32_t)i] += work[i];
+  for (size_t i = 0; i < n; ++i) gwork[group_of(i)] += work[i];
   std::vector<uint32_t> shard_of_group(n_groups);
   if ((rc = sfc_shard_plan(gwork.data(), n_groups, nd, shard_of_group.data()))) return rc;
-  // ---- per shard: pair list + compacted arena ----
+  // ---- per shard: pair list, then a compacted copy of just its sequences in pinned staging ----
   struct Shard {
     std::vector<uint32_t> idx;
-    std::vector<sfc_pair> pairs;
-    std::vector<uint8_t> arena;
-    std::vector<int32_t> scores, status;
+    size_t arena_bytes = 0;
     std::vector<uint32_t> ops;
     std::vector<uint64_t> ops_off;
     int rc = 0;
@@ -1020,66 +1049,76 @@ extern "C" int sfc_multi_align_batch(sfc_multi* m, const sfc_penalties* pen, con
   for (size_t i = 0; i < n; ++i) {
     const sfc_pair& p = pairs[i];
     if (p.pattern_off + p.pattern_len > arena_len || p.text_off + p.text_len > arena_len) { m->err = "sequence outside arena"; return SFC_ERR_INVALID; }
-    sh[shard_of_group[group_of_pair ? group_of_pair[i] : (uint32_t)i]].idx.push_back((uint32_t)i);
+    sh[shard_of_group[group_of(i)]].idx.push_back((uint32_t)i);
   }
-  for (Shard& s : sh) {
-    s.pairs.reserve(s.idx.size());
-    uint64_t last_t_off = ~0ull, last_t_new = 0;  // consecutive pairs usually share their text (one read flank, several alleles)
+  for (int d = 0; d < nd; ++d) {
+    Shard& s = sh[(size_t)d];
+    sfc_multi::Stage& st = m->stage[(size_t)d];
+    uint64_t last_t_off = ~0ull;
     uint32_t last_t_len = 0;
-    for (uint32_t i : s.idx) {
-      sfc_pair q = pairs[i];
-      if (q.text_off == last_t_off && q.text_len == last_t_len) q.text_off = last_t_new;
-      else {
-        last_t_off = q.text_off; last_t_len = q.text_len; last_t_new = s.arena.size();
-        s.arena.insert(s.arena.end(), arena + q.text_off, arena + q.text_off + q.text_len);
-        q.text_off = last_t_new;
-      }
-      const uint64_t pn = s.arena.size();
-      s.arena.insert(s.arena.end(), arena + q.pattern_off, arena + q.pattern_off + q.pattern_len);
-      q.pattern_off = pn;
-      s.pairs.push_back(q);
+    size_t bytes = 0;
+    for (uint32_t i : s.idx) {  // pass 1: size (consecutive pairs usually share their text: one read flank, several alleles)
+      const sfc_pair& q = pairs[i];
+      if (!(q.text_off == last_t_off && q.text_len == last_t_len)) { bytes += q.text_len; last_t_off = q.text_off; last_t_len = q.text_len; }
+      bytes += q.pattern_len;
     }
-    s.scores.resize(s.idx.size());
-    s.status.resize(s.idx.size());
-    if (want_cigar) { s.ops_off.resize(s.idx.size() + 1); s.ops.resize(std::max<size_t>(s.idx.size() * 64, 1 << 16)); }
+    if (pinned_reserve(st.arena, st.arena_cap, bytes) || pinned_reserve(st.pairs, st.pairs_cap, s.idx.size()) ||
+        pinned_reserve(st.scores, st.scores_cap, s.idx.size()) || pinned_reserve(st.status, st.status_cap, s.idx.size())) {
+      m->err = "pinned staging allocation failed";
+      return SFC_ERR_OOM;
+    }
+    s.arena_bytes = bytes;
   }
-  // ---- one submitter thread per GPU ----
+  // ---- one submitter thread per GPU: compaction (pass 2), upload, kernels, download ----
   std::vector<std::thread> th;
   for (int d = 0; d < nd; ++d) {
     th.emplace_back([&, d]() {
       Shard& s = sh[(size_t)d];
+      sfc_multi::Stage& st = m->stage[(size_t)d];
       m->kernel_ms[(size_t)d] = 0.0;
       if (s.idx.empty()) return;
+      uint64_t last_t_off = ~0ull, last_t_new = 0, pos = 0;
+      uint32_t last_t_len = 0;
+      for (size_t j = 0; j < s.idx.size(); ++j) {
+        sfc_pair q = pairs[s.idx[j]];
+        if (q.text_off == last_t_off && q.text_len == last_t_len) q.text_off = last_t_new;
+        else {
+          last_t_off = q.text_off; last_t_len = q.text_len; last_t_new = pos;
+          memcpy(st.arena + pos, arena + q.text_off, q.text_len);
+          q.text_off = pos; pos += q.text_len;
+        }
+        memcpy(st.arena + pos, arena + q.pattern_off, q.pattern_len);
+        q.pattern_off = pos; pos += q.pattern_len;
+        st.pairs[j] = q;
+      }
+      if (want_cigar) { s.ops_off.resize(s.idx.size() + 1); s.ops.resize(std::max<size_t>(s.idx.size() * 64, 1 << 16)); }
       sfc_ctx* c = m->ctx[(size_t)d];
-      s.rc = sfc_batch_upload(c, s.arena.data(), s.arena.size(), s.pairs.data(), s.pairs.size());
+      s.rc = sfc_batch_upload(c, st.arena, s.arena_bytes, st.pairs, s.idx.size());
       if (!s.rc) s.rc = sfc_batch_run(c, pen, want_cigar);
       if (!s.rc) {
-        s.rc = sfc_batch_download(c, s.scores.data(), s.status.data(), want_cigar ? s.ops.data() : nullptr, s.ops.size(),
+        s.rc = sfc_batch_download(c, st.scores, st.status, want_cigar ? s.ops.data() : nullptr, s.ops.size(),
                                   want_cigar ? s.ops_off.data() : nullptr);
         if (s.rc == SFC_ERR_CAPACITY) {
           s.ops.resize((size_t)s.ops_off[s.idx.size()] + 16);
-          s.rc = sfc_batch_download(c, s.scores.data(), s.status.data(), s.ops.data(), s.ops.size(), s.ops_off.data());
+          s.rc = sfc_batch_download(c, st.scores, st.status, s.ops.data(), s.ops.size(), s.ops_off.data());
         }
       }
-      sfc_batch_stats st;
-      if (!sfc_batch_get_stats(c, &st)) m->kernel_ms[(size_t)d] = st.kernel_ms;
+      if (!s.rc) {  // host-side gather of this shard's integer results into the caller's pair order
+        for (size_t j = 0; j < s.idx.size(); ++j) { scores[s.idx[j]] = st.scores[j]; status[s.idx[j]] = st.status[j]; }
+      }
+      sfc_batch_stats bs;
+      if (!sfc_batch_get_stats(c, &bs)) m->kernel_ms[(size_t)d] = bs.kernel_ms;
     });
   }
   for (auto& t : th) t.join();
   for (int d = 0; d < nd; ++d) {
     if (sh[(size_t)d].rc) { m->err = std::string("device ") + std::to_string(d) + ": " + sfc_last_error(m->ctx[(size_t)d]); return sh[(size_t)d].rc; }
   }
-  // ---- host-side gather in the caller's pair order ----
-  std::vector<uint32_t> where(n);  // position inside its shard
-  std::vector<uint8_t> shard_of_pair(n);
-  for (int d = 0; d < nd; ++d)
-    for (size_t j = 0; j < sh[(size_t)d].idx.size(); ++j) {
-      const uint32_t i = sh[(size_t)d].idx[j];
-      where[i] = (uint32_t)j; shard_of_pair[i] = (uint8_t)d;
-      scores[i] = sh[(size_t)d].scores[j];
-      status[i] = sh[(size_t)d].status[j];
-    }
   if (want_cigar) {
+    std::vector<uint32_t> where(n);
+    std::vector<uint8_t> shard_of_pair(n);
+    for (int d = 0; d < nd; ++d)
+      for (size_t j = 0; j < sh[(size_t)d].idx.size(); ++j) { where[sh[(size_t)d].idx[j]] = (uint32_t)j; shard_of_pair[sh[(size_t)d].idx[j]] = (uint8_t)d; }
     uint64_t acc = 0;
     for (size_t i = 0; i < n; ++i) {
       const Shard& s = sh[shard_of_pair[i]];
@@ -1090,8 +1129,8 @@ extern "C" int sfc_multi_align_batch(sfc_multi* m, const sfc_penalties* pen, con
     if (acc > ops_cap || (!ops_rle && acc)) { m->err = "ops buffer too small"; return SFC_ERR_CAPACITY; }
     for (size_t i = 0; i < n; ++i) {
       const Shard& s = sh[shard_of_pair[i]];
-      const uint64_t b = s.ops_off[where[i]], e = s.ops_off[where[i] + 1];
-      if (e > b) memcpy(ops_rle + ops_off[i], s.ops.data() + b, (size_t)(e - b) * 4);
+      const uint64_t b0 = s.ops_off[where[i]], e0 = s.ops_off[where[i] + 1];
+      if (e0 > b0) memcpy(ops_rle + ops_off[i], s.ops.data() + b0, (size_t)(e0 - b0) * 4);
     }
   }
   return SFC_OK;
