@@ -334,19 +334,23 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
 
     // slot bases per component (row index == slot index); all row offsets are 32-bit element offsets into rings
     const int sbM = 0, sbI1 = P.nM, sbD1 = P.nM + P.nG1, sbI2 = P.nM + 2 * P.nG1, sbD2 = P.nM + 2 * P.nG1 + P.nG2;
-    auto slot_of = [&](int c, int sc) -> int {
-      switch (c) {
-        case K2_C_M: return sbM + sc % P.nM;
-        case K2_C_I1: return sbI1 + sc % P.nG1;
-        case K2_C_D1: return sbD1 + sc % P.nG1;
-        case K2_C_I2: return sbI2 + sc % P.nG2;
-        default: return sbD2 + sc % P.nG2;
+    // slot (== ring row) of component c at score `sc` <= s_now: (s_now mod depth) is kept incrementally in cur* because
+    // an integer modulo by a run-time value costs ~25 instructions and a score step needs a dozen of them
+    int curM = 0, curG1 = 0, curG2 = 0;
+    auto slot_of = [&](int c, int sc, int s_now) -> int {
+      const int back = s_now - sc;  // 0 <= back < depth for every row that is still in the ring
+      if (c == K2_C_M) { const int v = curM - min(back, P.nM - 1); return sbM + v + (v < 0 ? P.nM : 0); }
+      if (c == K2_C_I1 || c == K2_C_D1) {
+        const int v = curG1 - min(back, P.nG1 - 1);
+        return (c == K2_C_I1 ? sbI1 : sbD1) + v + (v < 0 ? P.nG1 : 0);
       }
+      const int v = curG2 - min(back, P.nG2 - 1);
+      return (c == K2_C_I2 ? sbI2 : sbD2) + v + (v < 0 ? P.nG2 : 0);
     };
-    auto get = [&](int c, int sc) -> K2Range {
+    auto get = [&](int c, int sc, int s_now) -> K2Range {
       K2Range r; r.lo = 1; r.hi = -1;
       if (sc < 0) return r;
-      const int sl = slot_of(c, sc);
+      const int sl = slot_of(c, sc, s_now);
       r.lo = meta[2 * sl]; r.hi = meta[2 * sl + 1];
       return r;
     };
@@ -355,7 +359,8 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
     int s = 0, end_k = 0;
     bool done = false;
     K2_TICK(t_setup);
-    for (;; ++s) {
+    for (;; ++s, curM = (curM + 1 == P.nM ? 0 : curM + 1), curG1 = (curG1 + 1 == P.nG1 ? 0 : curG1 + 1),
+                curG2 = (curG2 + 1 == P.nG2 ? 0 : curG2 + 1)) {
       if (s > S_cap) { res_status = -7; break; }
       // ---- source wavefronts ----
       const int s_mx = s - P.x;
@@ -367,12 +372,12 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
       int lo = INT_MAX, hi = INT_MIN;
       if (s == 0) { lo = -pr.pbf; hi = pr.tbf; }
       else {
-        MX = get(K2_C_M, s_mx); MO1 = get(K2_C_M, s_o1);
+        MX = get(K2_C_M, s_mx, s); MO1 = get(K2_C_M, s_o1, s);
         if (MX.any()) { lo = min(lo, MX.lo); hi = max(hi, MX.hi); }
         if (MO1.any()) { lo = min(lo, MO1.lo - 1); hi = max(hi, MO1.hi + 1); }
         if (AFF) {
-          MO2 = get(K2_C_M, s_o2); I1E = get(K2_C_I1, s_e1); D1E = get(K2_C_D1, s_e1);
-          I2E = get(K2_C_I2, s_e2); D2E = get(K2_C_D2, s_e2);
+          MO2 = get(K2_C_M, s_o2, s); I1E = get(K2_C_I1, s_e1, s); D1E = get(K2_C_D1, s_e1, s);
+          I2E = get(K2_C_I2, s_e2, s); D2E = get(K2_C_D2, s_e2, s);
           if (MO2.any()) { lo = min(lo, MO2.lo - 1); hi = max(hi, MO2.hi + 1); }
           if (I1E.any()) { lo = min(lo, I1E.lo + 1); hi = max(hi, I1E.hi + 1); }
           if (D1E.any()) { lo = min(lo, D1E.lo - 1); hi = max(hi, D1E.hi - 1); }
@@ -382,7 +387,7 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
       }
       if (lo > hi) {  // wavefront s does not exist
         if (tid == 0) {  // every CTA marks its own copy
-          for (int c = 0; c < (AFF ? 5 : 1); ++c) { meta[2 * slot_of(c, s)] = 1; meta[2 * slot_of(c, s) + 1] = -1; }
+          for (int c = 0; c < (AFF ? 5 : 1); ++c) { meta[2 * slot_of(c, s, s)] = 1; meta[2 * slot_of(c, s, s) + 1] = -1; }
         }
         __syncthreads();
         continue;
@@ -411,12 +416,12 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
       const T* __restrict__ R = rings;
       // unsigned element offsets of the row starts (row r, diagonal k lives at r*Wp + kbase + k >= 0)
       const unsigned uWp = (unsigned)Wp;
-      const unsigned qMX = (unsigned)slot_of(K2_C_M, max(s_mx, 0)) * uWp, qMO1 = (unsigned)slot_of(K2_C_M, max(s_o1, 0)) * uWp;
-      const unsigned qMO2 = (unsigned)slot_of(K2_C_M, max(s_o2, 0)) * uWp;
-      const unsigned qI1E = (unsigned)slot_of(K2_C_I1, max(s_e1, 0)) * uWp, qD1E = (unsigned)slot_of(K2_C_D1, max(s_e1, 0)) * uWp;
-      const unsigned qI2E = (unsigned)slot_of(K2_C_I2, max(s_e2, 0)) * uWp, qD2E = (unsigned)slot_of(K2_C_D2, max(s_e2, 0)) * uWp;
-      const unsigned wM = (unsigned)slot_of(K2_C_M, s) * uWp, wI1 = (unsigned)slot_of(K2_C_I1, s) * uWp, wD1 = (unsigned)slot_of(K2_C_D1, s) * uWp;
-      const unsigned wI2 = (unsigned)slot_of(K2_C_I2, s) * uWp, wD2 = (unsigned)slot_of(K2_C_D2, s) * uWp;
+      const unsigned qMX = (unsigned)slot_of(K2_C_M, max(s_mx, 0), s) * uWp, qMO1 = (unsigned)slot_of(K2_C_M, max(s_o1, 0), s) * uWp;
+      const unsigned qMO2 = (unsigned)slot_of(K2_C_M, max(s_o2, 0), s) * uWp;
+      const unsigned qI1E = (unsigned)slot_of(K2_C_I1, max(s_e1, 0), s) * uWp, qD1E = (unsigned)slot_of(K2_C_D1, max(s_e1, 0), s) * uWp;
+      const unsigned qI2E = (unsigned)slot_of(K2_C_I2, max(s_e2, 0), s) * uWp, qD2E = (unsigned)slot_of(K2_C_D2, max(s_e2, 0), s) * uWp;
+      const unsigned wM = (unsigned)slot_of(K2_C_M, s, s) * uWp, wI1 = (unsigned)slot_of(K2_C_I1, s, s) * uWp, wD1 = (unsigned)slot_of(K2_C_D1, s, s) * uWp;
+      const unsigned wI2 = (unsigned)slot_of(K2_C_I2, s, s) * uWp, wD2 = (unsigned)slot_of(K2_C_D2, s, s) * uWp;
       unsigned char* btrow = bt + bt_used;  // byte index = (k + kbase) - 4*g_lo
       const int cMX = MX.cnt(), cMO1 = MO1.cnt(), cMO2 = MO2.cnt(), cI1E = I1E.cnt(), cD1E = D1E.cnt(),
                 cI2E = I2E.cnt(), cD2E = D2E.cnt();
@@ -609,7 +614,7 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
         const int ncomp = AFF ? 5 : 1;
         for (int task = crank * NW + warp; task < 2 * ncomp; task += C * NW) {
           const int c = task >> 1, side = task & 1;
-          const int sl = slot_of(c, s);
+          const int sl = slot_of(c, s, s);
           int found = side ? -1 : 1;  // empty encoding: lo = 1, hi = -1
           if (c == K2_C_M || s > 0) {
             if ((c == K2_C_I2 || c == K2_C_D2) && !has2) {
@@ -651,7 +656,7 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
     if (done) {
       csync();  // rowoff/rowlo/bt/oM of the last step visible to warp 0 of rank 0
       if (crank == 0 && warp == 0) {
-        const T* oM = rings + (size_t)slot_of(K2_C_M, s) * Wp + kbase;
+        const T* oM = rings + (size_t)slot_of(K2_C_M, s, s) * Wp + kbase;
         const int end_off = oM[end_k];
         int k0 = 0, nb = 0, bad = 0;
         if (lane == 0) {

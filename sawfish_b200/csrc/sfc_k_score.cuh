@@ -101,18 +101,20 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
     k1_gsync<WPP>(group);
 
     int s = 0, res_status = 0, res_score = 0;
-    for (;; ++s) {
+    int slot_s = 0;  // s modulo rd, kept incrementally (an integer modulo by a run-time value costs ~25 instructions)
+    for (;; ++s, slot_s = (slot_s + 1 == rd ? 0 : slot_s + 1)) {
       if (s > P.max_score) { res_status = -7; break; }
       int lo, hi, lox = 1, hix = -1, loi = 1, hii = -1;
       const int sx = s - P.x, si = s - P.ip;
+      const int slot_x = slot_s - P.x + (slot_s - P.x < 0 ? rd : 0), slot_i = slot_s - P.ip + (slot_s - P.ip < 0 ? rd : 0);
       if (s == 0) {
         lo = -pr.pbf; hi = pr.tbf;
       } else {
-        if (sx >= 0) { lox = meta[2 * (sx % rd)]; hix = meta[2 * (sx % rd) + 1]; }
-        if (si >= 0) { loi = meta[2 * (si % rd)]; hii = meta[2 * (si % rd) + 1]; }
+        if (sx >= 0) { lox = meta[2 * slot_x]; hix = meta[2 * slot_x + 1]; }
+        if (si >= 0) { loi = meta[2 * slot_i]; hii = meta[2 * slot_i + 1]; }
         const bool hasx = lox <= hix, hasi = loi <= hii;
         if (!hasx && !hasi) {  // wavefront s does not exist
-          if (g == 0) { meta[2 * (s % rd)] = 1; meta[2 * (s % rd) + 1] = -1; }
+          if (g == 0) { meta[2 * slot_s] = 1; meta[2 * slot_s + 1] = -1; }
           k1_gsync<WPP>(group);
           continue;
         }
@@ -120,12 +122,12 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
         lo = max(min(hasx ? lox : INT_MAX, hasi ? loi - 1 : INT_MAX), -plen);
         hi = min(max(hasx ? hix : INT_MIN, hasi ? hii + 1 : INT_MIN), tlen);
       }
-      if (g == 0) { meta[2 * (s % rd)] = lo; meta[2 * (s % rd) + 1] = hi; cells_acc += (unsigned long long)(hi - lo + 1); }
+      if (g == 0) { meta[2 * slot_s] = lo; meta[2 * slot_s + 1] = hi; cells_acc += (unsigned long long)(hi - lo + 1); }
       const int ilo = max(max(lox, loi + 1), lo), ihi = min(min(hix, hii - 1), hi);  // every read in range, every cell active
       const int cntx = max(hix - lox + 1, 0), cnti = max(hii - loi + 1, 0);
-      const int32_t* rowX = ring + (size_t)((sx >= 0 ? sx : 0) % rd) * wcap;
-      const int32_t* rowI = ring + (size_t)((si >= 0 ? si : 0) % rd) * wcap;
-      int32_t* rowO = ring + (size_t)(s % rd) * wcap;
+      const int32_t* rowX = ring + slot_x * wcap;
+      const int32_t* rowI = ring + slot_i * wcap;
+      int32_t* rowO = ring + slot_s * wcap;
       int term_k = INT_MAX;
       const int g_lo = (lo + kbase) >> 2, g_hi = (hi + kbase) >> 2;
 
