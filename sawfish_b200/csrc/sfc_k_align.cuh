@@ -142,7 +142,9 @@ struct K2Rows {  // row pointers (element 0 of each ring row) of the sources / d
 // lies inside that source's live range, so there are no guards and no predicates — straight-line code.
 __device__ __forceinline__ void k2_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-template <bool AFF, bool HAS2, typename T>
+// HAS2: piece-2 sources exist at this score; MO2: this chunk lies inside the live range of M[s-o2'-e2'] (outside it the
+// gap-open-2 candidates are null and that row is neither read nor prefetched).
+template <bool AFF, bool HAS2, bool MO2, typename T>
 __device__ __forceinline__ void k2_fast_chunk(unsigned char* __restrict__ btq, const K2Rows<T>& q, unsigned e0, unsigned pf, int k0, int lane,
                                               const uint2* __restrict__ wp, const uint2* __restrict__ wt,
                                               int plen, int tlen, int pef, int tef, int& term_k) {
@@ -152,7 +154,7 @@ __device__ __forceinline__ void k2_fast_chunk(unsigned char* __restrict__ btq, c
     k2_prefetch_l2(q.pMX + e0 + pf); k2_prefetch_l2(q.pMO1 + e0 + pf);
     if (AFF) {
       k2_prefetch_l2(q.pI1E + e0 + pf); k2_prefetch_l2(q.pD1E + e0 + pf);
-      if (HAS2) { k2_prefetch_l2(q.pMO2 + e0 + pf); k2_prefetch_l2(q.pI2E + e0 + pf); k2_prefetch_l2(q.pD2E + e0 + pf); }
+      if (HAS2) { if (MO2) k2_prefetch_l2(q.pMO2 + e0 + pf); k2_prefetch_l2(q.pI2E + e0 + pf); k2_prefetch_l2(q.pD2E + e0 + pf); }
     }
   }
   K2Vec<T>::load(q.pMX + e0, mx);
@@ -170,13 +172,19 @@ __device__ __forceinline__ void k2_fast_chunk(unsigned char* __restrict__ btq, c
     if (lane == 31) d1r = q.pD1E[e0 + 4u];
     int32_t m2[4], a2[4], d2[4], m2l = WNULL, m2r = WNULL, a2l = WNULL, d2r = WNULL;
     if (HAS2) {
-      K2Vec<T>::load(q.pMO2 + e0, m2);
       K2Vec<T>::load(q.pI2E + e0, a2);
       K2Vec<T>::load(q.pD2E + e0, d2);
-      m2l = __shfl_up_sync(FULL, m2[3], 1); m2r = __shfl_down_sync(FULL, m2[0], 1);
       a2l = __shfl_up_sync(FULL, a2[3], 1); d2r = __shfl_down_sync(FULL, d2[0], 1);
-      if (lane == 0) { m2l = q.pMO2[e0 - 1u]; a2l = q.pI2E[e0 - 1u]; }
-      if (lane == 31) { m2r = q.pMO2[e0 + 4u]; d2r = q.pD2E[e0 + 4u]; }
+      if (lane == 0) a2l = q.pI2E[e0 - 1u];
+      if (lane == 31) d2r = q.pD2E[e0 + 4u];
+      if (MO2) {
+        K2Vec<T>::load(q.pMO2 + e0, m2);
+        m2l = __shfl_up_sync(FULL, m2[3], 1); m2r = __shfl_down_sync(FULL, m2[0], 1);
+        if (lane == 0) m2l = q.pMO2[e0 - 1u];
+        if (lane == 31) m2r = q.pMO2[e0 + 4u];
+      } else {
+        m2[0] = m2[1] = m2[2] = m2[3] = WNULL;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -413,6 +421,12 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
         }
         if (!ok || s == 0) { ilo = 1; ihi = 0; }
       }
+      // second interior: everything but M[s-o2'-e2'] in range (that row is ~120 diagonals narrower on both sides)
+      int ilo_b = 1, ihi_b = 0;
+      if (AFF && has2 && s > 0 && MX.any() && MO1.any() && I1E.any() && D1E.any() && I2E.any() && D2E.any()) {
+        ilo_b = max(max(MX.lo, MO1.lo + 1), max(max(I1E.lo + 1, D1E.lo - 1), max(I2E.lo + 1, D2E.lo - 1)));
+        ihi_b = min(min(MX.hi, MO1.hi - 1), min(min(I1E.hi + 1, D1E.hi - 1), min(I2E.hi + 1, D2E.hi - 1)));
+      }
       const T* __restrict__ R = rings;
       // unsigned element offsets of the row starts (row r, diagonal k lives at r*Wp + kbase + k >= 0)
       const unsigned uWp = (unsigned)Wp;
@@ -457,9 +471,17 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
         const int k0 = (int)e0 - kbase;
         if (s > 0 && (gb << 2) - kbase >= flo && (gb << 2) - kbase + 127 <= fhi) {  // interior chunk
           const unsigned pf = (gb + C * NW * 32 + 31 <= g_hi) ? (unsigned)(C * NW * 128) : 0u;  // next chunk of this warp, in elements
-          if (has2) k2_fast_chunk<AFF, true, T>(btq, rows, e0, pf, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
-          else k2_fast_chunk<AFF, false, T>(btq, rows, e0, pf, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+          if (has2) k2_fast_chunk<AFF, true, true, T>(btq, rows, e0, pf, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+          else k2_fast_chunk<AFF, false, false, T>(btq, rows, e0, pf, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
           continue;
+        }
+        if (AFF) {
+          const int kA2 = (gb << 2) - kbase, kB2 = kA2 + 127;
+          if (kA2 >= max(ilo_b, lo) && kB2 <= min(ihi_b, hi) && (!MO2.any() || kB2 + 1 < MO2.lo || kA2 - 1 > MO2.hi)) {
+            const unsigned pf = (gb + C * NW * 32 + 31 <= g_hi) ? (unsigned)(C * NW * 128) : 0u;
+            k2_fast_chunk<AFF, true, false, T>(btq, rows, e0, pf, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+            continue;
+          }
         }
         int32_t best[4], ins1[4], ins2[4], del1[4], del2[4];
         uint32_t ch[4];
