@@ -160,3 +160,28 @@ def test_single_process_multi_gpu_sharding(ctx):
             assert (multi.last_kernel_ms() > 0).all()  # every GPU got work
     finally:
         multi.close()
+
+
+def test_asymmetric_lengths_and_clips(ctx, oracle):
+    """Short pattern inside a long text and vice versa, zero / maximal / one-sided ends-free allowances."""
+    from sawfish_b200 import synth
+    from sawfish_b200.batch import PAIR_DTYPE
+    lin, aff = _pens()
+    rng = np.random.default_rng(12)
+    long_seq = synth.random_seq(rng, 6000)
+    short = synth.add_errors(rng, long_seq[2500:2740], 0.01)
+    mid = synth.add_errors(rng, np.concatenate([long_seq[1000:1800], long_seq[1900:2600]]), 0.002)
+    arena = np.concatenate([long_seq, short, mid])
+    oL, oS, oM = 0, len(long_seq), len(long_seq) + len(short)
+    nL, nS, nM = len(long_seq), len(short), len(mid)
+    rows = []
+    for (po, pn, to, tn) in [(oS, nS, oL, nL), (oL, nL, oS, nS), (oM, nM, oL, nL), (oL, nL, oM, nM), (oS, nS, oM, nM)]:
+        for ends in [(0, 0, 0, 0), (0, 0, tn, tn), (pn, pn, 0, 0), (pn // 2, 0, 0, tn // 2), (0, pn // 3, tn // 3, 0),
+                     (min(pn, tn) * 2 // 5,) * 4]:
+            ends = (min(ends[0], pn), min(ends[1], pn), min(ends[2], tn), min(ends[3], tn))
+            for rev in (0, 1):
+                rows.append((po, to, pn, tn) + ends + (rev,))
+    pairs = np.array(rows, dtype=PAIR_DTYPE)
+    compare_with_oracle(oracle, ctx, lin, arena, pairs, want_cigar=False)
+    compare_with_oracle(oracle, ctx, lin, arena, pairs, want_cigar=True)
+    compare_with_oracle(oracle, ctx, aff, arena, pairs, want_cigar=True)

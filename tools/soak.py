@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Soak test: many seeded batches of every shape through the CUDA path vs the oracle (run on the GPU box).
+usage: python tools/soak.py [seconds]"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import compare_with_oracle  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from sawfish_b200 import synth  # noqa: E402
+from sawfish_b200.batch import AlignContext, CONSENSUS_PENALTIES, LARGE_INDEL_PENALTIES  # noqa: E402
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+ctx = AlignContext(0)
+t0 = time.time()
+seed = 1000
+n_batches = n_pairs = 0
+while time.time() - t0 < budget:
+    seed += 1
+    kind = seed % 6
+    if kind == 0:
+        arena, pairs = synth.random_pairs(800, seed=seed, max_len=200)
+        jobs = [(CONSENSUS_PENALTIES, False), (CONSENSUS_PENALTIES, True), (LARGE_INDEL_PENALTIES, True)]
+        mode = O.MODE_LITERAL
+    elif kind == 1:
+        arena, pairs = synth.low_complexity_pairs(60, seed=seed, len_lo=200, len_hi=2500)
+        jobs = [(CONSENSUS_PENALTIES, False), (LARGE_INDEL_PENALTIES, True)]
+        mode = None
+    elif kind == 2:
+        arena, pairs, _ = synth.config2b_score_sv_flanks(1500, seed=seed)
+        jobs = [(CONSENSUS_PENALTIES, False)]
+        mode = None
+    elif kind == 3:
+        arena, pairs = synth.config3_refine_contigs(int(np.random.default_rng(seed).integers(1, 40)), seed=seed, two_region_frac=0.4)
+        jobs = [(LARGE_INDEL_PENALTIES, True)]
+        mode = None
+    elif kind == 4:
+        arena, pairs, _ = synth.config2_read_vs_haplotypes(int(np.random.default_rng(seed).integers(1, 6)), seed=seed, len_lo=1000,
+                                                            len_hi=9000, sv_hi=2500)
+        jobs = [(LARGE_INDEL_PENALTIES, True), (LARGE_INDEL_PENALTIES, False)]
+        mode = None
+    else:
+        arena, pairs = synth.config5_stress(1, seed=seed, len_lo=1500, len_hi=4000, div_lo=0.01, div_hi=0.05)
+        jobs = [(LARGE_INDEL_PENALTIES, True), (CONSENSUS_PENALTIES, True)]
+        mode = None
+    for narrow in (False, True):
+        if narrow:
+            os.environ["SFC_K2_NARROW"] = "1"
+        else:
+            os.environ.pop("SFC_K2_NARROW", None)
+        for pen, wc in jobs:
+            compare_with_oracle(O, ctx, pen, arena, pairs, want_cigar=wc, mode=mode)
+            n_batches += 1
+            n_pairs += len(pairs)
+print(f"soak ok: {n_batches} batches, {n_pairs} pairs, seeds 1001..{seed}, {time.time() - t0:.0f} s")
