@@ -185,3 +185,23 @@ def test_asymmetric_lengths_and_clips(ctx, oracle):
     compare_with_oracle(oracle, ctx, lin, arena, pairs, want_cigar=False)
     compare_with_oracle(oracle, ctx, lin, arena, pairs, want_cigar=True)
     compare_with_oracle(oracle, ctx, aff, arena, pairs, want_cigar=True)
+
+
+def test_ops_pool_growth_path(ctx, oracle):
+    """Enough CIGAR runs in one batch to overflow the initial device ops pool (1 Mi entries): the pairs that did not
+    fit are re-run with a larger pool (stats.retries > 0) and every result still matches the oracle."""
+    from sawfish_b200 import synth
+    from sawfish_b200.batch import PAIR_DTYPE, sawfish_clip
+    _, aff = _pens()
+    rng = np.random.default_rng(99)
+    chunks, rows, off = [], [], 0
+    for _ in range(9000):
+        t = synth.random_seq(rng, 900)
+        p = synth.add_errors(rng, t, 0.09)
+        chunks += [t, p]
+        c = sawfish_clip(len(p), len(t))
+        rows.append((off + len(t), off, len(p), len(t), c, c, c, c, 1))
+        off += len(t) + len(p)
+    arena, pairs = np.concatenate(chunks), np.array(rows, dtype=PAIR_DTYPE)
+    compare_with_oracle(oracle, ctx, aff, arena, pairs, want_cigar=True)
+    assert ctx.stats()["retries"] >= 1
