@@ -53,6 +53,7 @@ struct K2Params {
   uint32_t* out_len;            // [n]
   unsigned long long* cells;
   int win_cap;  // uint2 windows available in shared memory for both sequences together
+  int stages;   // cp.async stages per warp for the interior chunks (0 = load straight from global; int32 rings only)
   int max_score;
   unsigned long long* prof;  // optional phase timers (clock64 of thread 0): [0] cell loop [1] barriers+trim [2] backtrace [3] setup
 };
@@ -144,46 +145,121 @@ __device__ __forceinline__ void k2_prefetch_l2(const void* p) { asm volatile("pr
 
 // HAS2: piece-2 sources exist at this score; MO2: this chunk lies inside the live range of M[s-o2'-e2'] (outside it the
 // gap-open-2 candidates are null and that row is neither read nor prefetched).
-template <bool AFF, bool HAS2, bool MO2, typename T>
-__device__ __forceinline__ void k2_fast_chunk(unsigned char* __restrict__ btq, const K2Rows<T>& q, unsigned e0, unsigned pf, int k0, int lane,
+// ---- shared-memory staging of the interior chunks (int32 rings) ----
+// A warp's chunk needs, from each of up to 7 source rows, its 128 elements plus one neighbour on each side.  The
+// 16-byte units [e0w-4, e0w+132) of every row are copied global -> shared with cp.async (LDGSTS, L2 -> smem, no
+// registers held across the latency) one or two chunks ahead of the compute, so the ~1 us ring-load latency that
+// used to stall every chunk (45% of all warp samples: long scoreboard) overlaps the previous chunk's arithmetic.
+constexpr int K2_SE = 136;                                     // staged elements per row: 4 + 128 + 4
+enum { K2_SR_MX = 0, K2_SR_MO1, K2_SR_I1E, K2_SR_D1E, K2_SR_I2E, K2_SR_D2E, K2_SR_MO2, K2_SR_N };
+__device__ __forceinline__ void k2_cp16(const int32_t* smem_dst, const int32_t* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void k2_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void k2_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void k2_cp_wait_n(int n) {  // wait until at most n of this thread's groups are pending
+  if (n <= 0) k2_cp_wait<0>(); else if (n == 1) k2_cp_wait<1>(); else k2_cp_wait<2>();
+}
+// lane L copies its own group (unit L+1) of every needed row; lanes 0 / 31 also copy the unit left / right of the chunk
+template <bool AFF>
+__device__ __forceinline__ void k2_stage_issue(int32_t* stg, const K2Rows<int32_t>& q, unsigned e0w, bool has2, bool mo2, int lane) {
+  const unsigned eo = e0w + ((unsigned)lane << 2);
+  int32_t* d = stg + 4 + (lane << 2);
+  const bool lx = lane == 0 && e0w >= 4u;  // the leftmost boundary chunk can start at element 0 of the row
+  const bool ex = lx || (lane == 31);
+  const int xo = lane == 0 ? -4 : 4;
+  k2_cp16(d + K2_SR_MX * K2_SE, q.pMX + eo);
+  k2_cp16(d + K2_SR_MO1 * K2_SE, q.pMO1 + eo);
+  if (ex) k2_cp16(d + K2_SR_MO1 * K2_SE + xo, q.pMO1 + eo + xo);
+  if (AFF) {
+    k2_cp16(d + K2_SR_I1E * K2_SE, q.pI1E + eo);
+    k2_cp16(d + K2_SR_D1E * K2_SE, q.pD1E + eo);
+    if (lx) k2_cp16(d + K2_SR_I1E * K2_SE - 4, q.pI1E + eo - 4);
+    if (lane == 31) k2_cp16(d + K2_SR_D1E * K2_SE + 4, q.pD1E + eo + 4);
+    if (has2) {
+      k2_cp16(d + K2_SR_I2E * K2_SE, q.pI2E + eo);
+      k2_cp16(d + K2_SR_D2E * K2_SE, q.pD2E + eo);
+      if (lx) k2_cp16(d + K2_SR_I2E * K2_SE - 4, q.pI2E + eo - 4);
+      if (lane == 31) k2_cp16(d + K2_SR_D2E * K2_SE + 4, q.pD2E + eo + 4);
+      if (mo2) {
+        k2_cp16(d + K2_SR_MO2 * K2_SE, q.pMO2 + eo);
+        if (ex) k2_cp16(d + K2_SR_MO2 * K2_SE + xo, q.pMO2 + eo + xo);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void k2_lds4(const int32_t* p, int32_t (&o)[4]) {
+  const int4 v = *reinterpret_cast<const int4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+
+// STG: the sources were staged in shared memory at `stg` (this warp's stage, see k2_stage_issue) instead of being
+// loaded from global here.
+template <bool AFF, bool HAS2, bool MO2, bool STG, typename T>
+__device__ __forceinline__ void k2_fast_chunk(unsigned char* __restrict__ btq, const K2Rows<T>& q, const int32_t* __restrict__ stg,
+                                              unsigned e0, unsigned pf, int k0, int lane,
                                               const uint2* __restrict__ wp, const uint2* __restrict__ wt,
                                               int plen, int tlen, int pef, int tef, int& term_k) {
   int32_t mx[4], m1[4], best[4];
   uint32_t ch[4];
-  if (pf) {  // pull this warp's NEXT chunk of every source row towards L2 while the current chunk is computed
+  const int32_t* sb = STG ? stg + 4 + (lane << 2) : nullptr;
+  if (!STG && pf) {  // pull this warp's NEXT chunk of every source row towards L2 while the current chunk is computed
     k2_prefetch_l2(q.pMX + e0 + pf); k2_prefetch_l2(q.pMO1 + e0 + pf);
     if (AFF) {
       k2_prefetch_l2(q.pI1E + e0 + pf); k2_prefetch_l2(q.pD1E + e0 + pf);
       if (HAS2) { if (MO2) k2_prefetch_l2(q.pMO2 + e0 + pf); k2_prefetch_l2(q.pI2E + e0 + pf); k2_prefetch_l2(q.pD2E + e0 + pf); }
     }
   }
-  K2Vec<T>::load(q.pMX + e0, mx);
-  K2Vec<T>::load(q.pMO1 + e0, m1);
-  int32_t m1l = __shfl_up_sync(FULL, m1[3], 1), m1r = __shfl_down_sync(FULL, m1[0], 1);
-  if (lane == 0) m1l = q.pMO1[e0 - 1u];
-  if (lane == 31) m1r = q.pMO1[e0 + 4u];
+  int32_t m1l, m1r;
+  if (STG) {
+    k2_lds4(sb + K2_SR_MX * K2_SE, mx);
+    k2_lds4(sb + K2_SR_MO1 * K2_SE, m1);
+    m1l = sb[K2_SR_MO1 * K2_SE - 1]; m1r = sb[K2_SR_MO1 * K2_SE + 4];
+  } else {
+    K2Vec<T>::load(q.pMX + e0, mx);
+    K2Vec<T>::load(q.pMO1 + e0, m1);
+    m1l = __shfl_up_sync(FULL, m1[3], 1); m1r = __shfl_down_sync(FULL, m1[0], 1);
+    if (lane == 0) m1l = q.pMO1[e0 - 1u];
+    if (lane == 31) m1r = q.pMO1[e0 + 4u];
+  }
   int32_t ins1[4], del1[4], ins2[4], del2[4];
   if (AFF) {
-    int32_t a1[4], d1[4];
-    K2Vec<T>::load(q.pI1E + e0, a1);
-    K2Vec<T>::load(q.pD1E + e0, d1);
-    int32_t a1l = __shfl_up_sync(FULL, a1[3], 1), d1r = __shfl_down_sync(FULL, d1[0], 1);
-    if (lane == 0) a1l = q.pI1E[e0 - 1u];
-    if (lane == 31) d1r = q.pD1E[e0 + 4u];
+    int32_t a1[4], d1[4], a1l, d1r;
     int32_t m2[4], a2[4], d2[4], m2l = WNULL, m2r = WNULL, a2l = WNULL, d2r = WNULL;
-    if (HAS2) {
-      K2Vec<T>::load(q.pI2E + e0, a2);
-      K2Vec<T>::load(q.pD2E + e0, d2);
-      a2l = __shfl_up_sync(FULL, a2[3], 1); d2r = __shfl_down_sync(FULL, d2[0], 1);
-      if (lane == 0) a2l = q.pI2E[e0 - 1u];
-      if (lane == 31) d2r = q.pD2E[e0 + 4u];
-      if (MO2) {
-        K2Vec<T>::load(q.pMO2 + e0, m2);
-        m2l = __shfl_up_sync(FULL, m2[3], 1); m2r = __shfl_down_sync(FULL, m2[0], 1);
-        if (lane == 0) m2l = q.pMO2[e0 - 1u];
-        if (lane == 31) m2r = q.pMO2[e0 + 4u];
-      } else {
-        m2[0] = m2[1] = m2[2] = m2[3] = WNULL;
+    if (STG) {
+      k2_lds4(sb + K2_SR_I1E * K2_SE, a1); a1l = sb[K2_SR_I1E * K2_SE - 1];
+      k2_lds4(sb + K2_SR_D1E * K2_SE, d1); d1r = sb[K2_SR_D1E * K2_SE + 4];
+      if (HAS2) {
+        k2_lds4(sb + K2_SR_I2E * K2_SE, a2); a2l = sb[K2_SR_I2E * K2_SE - 1];
+        k2_lds4(sb + K2_SR_D2E * K2_SE, d2); d2r = sb[K2_SR_D2E * K2_SE + 4];
+        if (MO2) {
+          k2_lds4(sb + K2_SR_MO2 * K2_SE, m2);
+          m2l = sb[K2_SR_MO2 * K2_SE - 1]; m2r = sb[K2_SR_MO2 * K2_SE + 4];
+        } else {
+          m2[0] = m2[1] = m2[2] = m2[3] = WNULL;
+        }
+      }
+    } else {
+      K2Vec<T>::load(q.pI1E + e0, a1);
+      K2Vec<T>::load(q.pD1E + e0, d1);
+      a1l = __shfl_up_sync(FULL, a1[3], 1); d1r = __shfl_down_sync(FULL, d1[0], 1);
+      if (lane == 0) a1l = q.pI1E[e0 - 1u];
+      if (lane == 31) d1r = q.pD1E[e0 + 4u];
+      if (HAS2) {
+        K2Vec<T>::load(q.pI2E + e0, a2);
+        K2Vec<T>::load(q.pD2E + e0, d2);
+        a2l = __shfl_up_sync(FULL, a2[3], 1); d2r = __shfl_down_sync(FULL, d2[0], 1);
+        if (lane == 0) a2l = q.pI2E[e0 - 1u];
+        if (lane == 31) d2r = q.pD2E[e0 + 4u];
+        if (MO2) {
+          K2Vec<T>::load(q.pMO2 + e0, m2);
+          m2l = __shfl_up_sync(FULL, m2[3], 1); m2r = __shfl_down_sync(FULL, m2[0], 1);
+          if (lane == 0) m2l = q.pMO2[e0 - 1u];
+          if (lane == 31) m2r = q.pMO2[e0 + 4u];
+        } else {
+          m2[0] = m2[1] = m2[2] = m2[3] = WNULL;
+        }
       }
     }
 #pragma unroll
@@ -287,6 +363,12 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
   uint2* win = reinterpret_cast<uint2*>(k2_smem);
   int* meta = reinterpret_cast<int*>(win + P.win_cap);  // [nslots][2]
   int* misc = meta + 2 * nslots;                        // [0] pair idx, [1] terminating diagonal
+  // per-warp cp.async stages behind the fixed part (host: K2 plan_job sizes both)
+  constexpr bool CAN_STAGE = sizeof(T) == 4;
+  const int NR = AFF ? (int)K2_SR_N : 2;  // staged rows per chunk
+  const int S = CAN_STAGE ? P.stages : 0;
+  int32_t* wstg = reinterpret_cast<int32_t*>(k2_smem + (((size_t)P.win_cap * 8 + (size_t)nslots * 8 + 64 + 15) & ~(size_t)15)) +
+                  (size_t)(threadIdx.x >> 5) * S * NR * K2_SE;
   unsigned char* slab = P.slabs + (size_t)(blockIdx.x / C) * P.slab_bytes;
   int* misc0 = C > 1 ? cluster.map_shared_rank(misc, 0) : misc;  // rank 0's copy: work index + terminating diagonal
   unsigned long long cells_acc = 0;
@@ -464,24 +546,60 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
       rows.oM = rings + wM; rows.oI1 = rings + wI1; rows.oD1 = rings + wD1; rows.oI2 = rings + wI2; rows.oD2 = rings + wD2;
       unsigned char* btq = btrow - ((size_t)g_lo << 2);  // indexed by the element offset e = k + kbase
       const int flo = max(ilo, lo), fhi = min(ihi, hi);
-      for (int gb = g_lo + (crank * NW + warp) * 32; gb <= g_hi; gb += C * NW * 32) {
+      const int flo_b = max(ilo_b, lo), fhi_b = min(ihi_b, hi);
+      // 1: interior of every source; 2: interior of everything but M[s-o2'-e2'] and clear of it; 0: boundary (guarded)
+      auto kind_of = [&](int gb) -> int {
+        const int kA = (gb << 2) - kbase, kB = kA + 127;
+        if (s > 0 && kA >= flo && kB <= fhi) return 1;
+        if (AFF && kA >= flo_b && kB <= fhi_b && (!MO2.any() || kB + 1 < MO2.lo || kA - 1 > MO2.hi)) return 2;
+        return 0;
+      };
+      const int gstep = C * NW * 32;
+      int gi = g_lo + (crank * NW + warp) * 32, is = 0, cs = 0;  // next chunk to stage, its stage, stage of the chunk being computed
+      auto stage_next = [&]() {
+        if constexpr (CAN_STAGE) {
+          // boundary chunks are staged too (their out-of-range elements are masked by the range checks below)
+          if (gi <= g_hi && s > 0) k2_stage_issue<AFF>(wstg + is * NR * K2_SE, rows, (unsigned)gi << 2, has2, kind_of(gi) != 2, lane);
+          k2_cp_commit();  // one group per chunk slot (possibly empty) keeps the wait distance constant
+          gi += gstep;
+          is = is + 1 == S ? 0 : is + 1;
+        }
+      };
+      if (S > 0) for (int p = 0; p < S - 1; ++p) stage_next();
+      for (int gb = g_lo + (crank * NW + warp) * 32; gb <= g_hi; gb += gstep) {
         const int g = gb + lane;
         const bool gact = g <= g_hi;
         const unsigned e0 = (unsigned)g << 2;
         const int k0 = (int)e0 - kbase;
-        if (s > 0 && (gb << 2) - kbase >= flo && (gb << 2) - kbase + 127 <= fhi) {  // interior chunk
-          const unsigned pf = (gb + C * NW * 32 + 31 <= g_hi) ? (unsigned)(C * NW * 128) : 0u;  // next chunk of this warp, in elements
-          if (has2) k2_fast_chunk<AFF, true, true, T>(btq, rows, e0, pf, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
-          else k2_fast_chunk<AFF, false, false, T>(btq, rows, e0, pf, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+        const int kind = kind_of(gb);
+        const int32_t* stg = nullptr;
+        if (S > 0) {
+          __syncwarp();  // every lane is done reading the stage that is refilled now
+          stage_next();
+          k2_cp_wait_n(S - 1);
+          __syncwarp();  // the other lanes' copies of this chunk have landed too
+          stg = wstg + cs * NR * K2_SE;
+          cs = cs + 1 == S ? 0 : cs + 1;
+        }
+        if (kind == 1) {  // interior chunk
+          if (S > 0) {
+            if (has2) k2_fast_chunk<AFF, true, true, true, T>(btq, rows, stg, e0, 0u, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+            else k2_fast_chunk<AFF, false, false, true, T>(btq, rows, stg, e0, 0u, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+          } else {
+            const unsigned pf = (gb + gstep + 31 <= g_hi) ? (unsigned)(gstep << 2) : 0u;  // next chunk of this warp, in elements
+            if (has2) k2_fast_chunk<AFF, true, true, false, T>(btq, rows, nullptr, e0, pf, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+            else k2_fast_chunk<AFF, false, false, false, T>(btq, rows, nullptr, e0, pf, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+          }
           continue;
         }
-        if (AFF) {
-          const int kA2 = (gb << 2) - kbase, kB2 = kA2 + 127;
-          if (kA2 >= max(ilo_b, lo) && kB2 <= min(ihi_b, hi) && (!MO2.any() || kB2 + 1 < MO2.lo || kA2 - 1 > MO2.hi)) {
-            const unsigned pf = (gb + C * NW * 32 + 31 <= g_hi) ? (unsigned)(C * NW * 128) : 0u;
-            k2_fast_chunk<AFF, true, false, T>(btq, rows, e0, pf, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
-            continue;
+        if (AFF && kind == 2) {
+          if (S > 0) {
+            k2_fast_chunk<AFF, true, false, true, T>(btq, rows, stg, e0, 0u, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
+          } else {
+            const unsigned pf = (gb + gstep + 31 <= g_hi) ? (unsigned)(gstep << 2) : 0u;
+            k2_fast_chunk<AFF, true, false, false, T>(btq, rows, nullptr, e0, pf, k0, lane, wp, wt, plen, tlen, pr.pef, pr.tef, term_k);
           }
+          continue;
         }
         int32_t best[4], ins1[4], ins2[4], del1[4], del2[4];
         uint32_t ch[4];
@@ -496,9 +614,27 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
           const bool lastg = (g == g_hi);
           int32_t mx[4], m1[4], m1l, m1r, a1[4], a1l, d1[4], d1r, dummy = 0;
           int32_t m2[4], m2l = WNULL, m2r = WNULL, a2[4], a2l = WNULL, d2[4], d2r = WNULL;
+          if (S > 0) {  // staged: garbage outside the live ranges, masked below (boundary chunks are never `fast`)
+            const int32_t* sb = stg + 4 + (lane << 2);
+            k2_lds4(sb + K2_SR_MX * K2_SE, mx);
+            k2_lds4(sb + K2_SR_MO1 * K2_SE, m1); m1l = sb[K2_SR_MO1 * K2_SE - 1]; m1r = sb[K2_SR_MO1 * K2_SE + 4];
+            if (AFF) {
+              k2_lds4(sb + K2_SR_I1E * K2_SE, a1); a1l = sb[K2_SR_I1E * K2_SE - 1];
+              k2_lds4(sb + K2_SR_D1E * K2_SE, d1); d1r = sb[K2_SR_D1E * K2_SE + 4];
+              if (has2) {
+                k2_lds4(sb + K2_SR_MO2 * K2_SE, m2); m2l = sb[K2_SR_MO2 * K2_SE - 1]; m2r = sb[K2_SR_MO2 * K2_SE + 4];
+                k2_lds4(sb + K2_SR_I2E * K2_SE, a2); a2l = sb[K2_SR_I2E * K2_SE - 1];
+                k2_lds4(sb + K2_SR_D2E * K2_SE, d2); d2r = sb[K2_SR_D2E * K2_SE + 4];
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m2[j] = a2[j] = d2[j] = WNULL;
+              }
+            }
+          } else {
           load_row(qMX, e0, gact, lastg, false, false, mx, dummy, dummy);
           load_row(qMO1, e0, gact, lastg, true, true, m1, m1l, m1r);
-          if (AFF) {
+          }
+          if (AFF && S == 0) {
             load_row(qI1E, e0, gact, lastg, true, false, a1, a1l, dummy);
             load_row(qD1E, e0, gact, lastg, false, true, d1, dummy, d1r);
             if (has2) {
@@ -509,7 +645,7 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) m2[j] = a2[j] = d2[j] = WNULL;
             }
-          } else {
+          } else if (!AFF) {
             a1l = d1r = WNULL;
 #pragma unroll
             for (int j = 0; j < 4; ++j) a1[j] = d1[j] = m2[j] = a2[j] = d2[j] = WNULL;

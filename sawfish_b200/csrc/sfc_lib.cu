@@ -497,7 +497,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     }
 
     // size one job's launch: returns grid (in clusters), slab bytes, shared bytes, win_cap
-    struct Plan { size_t n_cl, slab, smem, max_fixed; int win_cap; bool wide; };
+    struct Plan { size_t n_cl, slab, smem, max_fixed; int win_cap, stages; bool wide; };
     auto plan_job = [&](const std::vector<uint32_t>& list, int threads, int C, size_t budget, int divisor, Plan* pl) -> int {
       size_t max_fixed = 0, max_win = 0, max_W = 0;
       bool wide = false;
@@ -517,9 +517,17 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
         max_win = std::max(max_win, (size_t)(d.plen >> 3) + (d.tlen >> 3) + 2);
         max_W = std::max(max_W, Wp);
       }
-      const size_t smem = std::min(max_win * 8 + (size_t)nslots * 8 + 64, c->smem_optin);
+      const size_t base = std::min(max_win * 8 + (size_t)nslots * 8 + 64, c->smem_optin);
+      pl->win_cap = (int)((base - (size_t)nslots * 8 - 64) / 8);
+      // cp.async stages for the interior chunks (int32 rings): two per warp when shared memory allows, else one, else none
+      const size_t fixed_sm = ((size_t)pl->win_cap * 8 + (size_t)nslots * 8 + 64 + 15) & ~(size_t)15;
+      const size_t per_stage = (size_t)(threads / 32) * (a.metric == 1 ? K2_SR_N : 2) * K2_SE * 4;
+      int stages = wide ? 2 : 0;
+      if (const char* e = getenv("SFC_K2_STAGES")) stages = wide ? std::max(0, std::min(3, atoi(e))) : 0;  // experiment knob
+      while (stages > 0 && fixed_sm + stages * per_stage > c->smem_optin) --stages;
+      pl->stages = stages;
+      const size_t smem = stages ? fixed_sm + stages * per_stage : base;
       pl->smem = smem;
-      pl->win_cap = (int)((smem - (size_t)nslots * 8 - 64) / 8);
       pl->max_fixed = max_fixed;
       // always the device maximum (see launch_k1): per-device attribute shared by every ctx / thread / job
       CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
@@ -561,6 +569,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       P.out_len = (uint32_t*)c->d_outlen.p;
       P.cells = (unsigned long long*)(misc + 2);
       P.win_cap = pl.win_cap;
+      P.stages = pl.stages;
       P.max_score = INT_MAX / 4;
       P.prof = getenv("SFC_K2_PROF") ? (unsigned long long*)(misc + 40) : nullptr;
       cudaLaunchConfig_t cfg = {};

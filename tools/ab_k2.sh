@@ -1,0 +1,12 @@
+#!/bin/bash
+# A/B runs of K2 variants (writes gpurun_out/ab_k2.log)
+mkdir -p gpurun_out
+{
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+for st in 2 3; do
+  echo "== stages $st"; SFC_K2_STAGES=$st python tools/bench_summary.py --workload config2 --no-cpu-baseline
+done
+echo "== stages 2 config3"; python tools/bench_summary.py --workload config3 --no-cpu-baseline
+echo "== prof"; SFC_K2_PROF=1 python bench.py --workload config2 --no-cpu-baseline --steps 2 --warmup 1 2>&1 | grep "k2 prof" | tail -1
+} > gpurun_out/ab_k2.log 2>&1
+cat gpurun_out/ab_k2.log
