@@ -134,9 +134,10 @@ __device__ __forceinline__ int k2_extend_more(const uint2* __restrict__ wp, cons
 }
 
 template <typename T>
-struct K2Rows {  // row pointers (element 0 of each ring row) of the sources / destinations of one score step
-  const T *pMX, *pMO1, *pMO2, *pI1E, *pD1E, *pI2E, *pD2E;
-  T *oM, *oI1, *oD1, *oI2, *oD2;
+struct K2Rows {  // 32-bit element offsets (from R) of the source / destination ring rows of one score step
+  T* R;
+  unsigned pMX, pMO1, pMO2, pI1E, pD1E, pI2E, pD2E;
+  unsigned oM, oI1, oD1, oI2, oD2;
 };
 
 // One interior chunk (128 diagonals per warp, 4 per thread): every lane is active and every read of every source
@@ -169,22 +170,22 @@ __device__ __forceinline__ void k2_stage_issue(int32_t* stg, const K2Rows<int32_
   const bool lx = lane == 0 && e0w >= 4u;  // the leftmost boundary chunk can start at element 0 of the row
   const bool ex = lx || (lane == 31);
   const int xo = lane == 0 ? -4 : 4;
-  k2_cp16(d + K2_SR_MX * K2_SE, q.pMX + eo);
-  k2_cp16(d + K2_SR_MO1 * K2_SE, q.pMO1 + eo);
-  if (ex) k2_cp16(d + K2_SR_MO1 * K2_SE + xo, q.pMO1 + eo + xo);
+  k2_cp16(d + K2_SR_MX * K2_SE, q.R + (q.pMX + eo));
+  k2_cp16(d + K2_SR_MO1 * K2_SE, q.R + (q.pMO1 + eo));
+  if (ex) k2_cp16(d + K2_SR_MO1 * K2_SE + xo, q.R + (q.pMO1 + eo + (unsigned)xo));
   if (AFF) {
-    k2_cp16(d + K2_SR_I1E * K2_SE, q.pI1E + eo);
-    k2_cp16(d + K2_SR_D1E * K2_SE, q.pD1E + eo);
-    if (lx) k2_cp16(d + K2_SR_I1E * K2_SE - 4, q.pI1E + eo - 4);
-    if (lane == 31) k2_cp16(d + K2_SR_D1E * K2_SE + 4, q.pD1E + eo + 4);
+    k2_cp16(d + K2_SR_I1E * K2_SE, q.R + (q.pI1E + eo));
+    k2_cp16(d + K2_SR_D1E * K2_SE, q.R + (q.pD1E + eo));
+    if (lx) k2_cp16(d + K2_SR_I1E * K2_SE - 4, q.R + (q.pI1E + eo - 4u));
+    if (lane == 31) k2_cp16(d + K2_SR_D1E * K2_SE + 4, q.R + (q.pD1E + eo + 4u));
     if (has2) {
-      k2_cp16(d + K2_SR_I2E * K2_SE, q.pI2E + eo);
-      k2_cp16(d + K2_SR_D2E * K2_SE, q.pD2E + eo);
-      if (lx) k2_cp16(d + K2_SR_I2E * K2_SE - 4, q.pI2E + eo - 4);
-      if (lane == 31) k2_cp16(d + K2_SR_D2E * K2_SE + 4, q.pD2E + eo + 4);
+      k2_cp16(d + K2_SR_I2E * K2_SE, q.R + (q.pI2E + eo));
+      k2_cp16(d + K2_SR_D2E * K2_SE, q.R + (q.pD2E + eo));
+      if (lx) k2_cp16(d + K2_SR_I2E * K2_SE - 4, q.R + (q.pI2E + eo - 4u));
+      if (lane == 31) k2_cp16(d + K2_SR_D2E * K2_SE + 4, q.R + (q.pD2E + eo + 4u));
       if (mo2) {
-        k2_cp16(d + K2_SR_MO2 * K2_SE, q.pMO2 + eo);
-        if (ex) k2_cp16(d + K2_SR_MO2 * K2_SE + xo, q.pMO2 + eo + xo);
+        k2_cp16(d + K2_SR_MO2 * K2_SE, q.R + (q.pMO2 + eo));
+        if (ex) k2_cp16(d + K2_SR_MO2 * K2_SE + xo, q.R + (q.pMO2 + eo + (unsigned)xo));
       }
     }
   }
@@ -205,10 +206,10 @@ __device__ __forceinline__ void k2_fast_chunk(unsigned char* __restrict__ btq, c
   uint32_t ch[4];
   const int32_t* sb = STG ? stg + 4 + (lane << 2) : nullptr;
   if (!STG && pf) {  // pull this warp's NEXT chunk of every source row towards L2 while the current chunk is computed
-    k2_prefetch_l2(q.pMX + e0 + pf); k2_prefetch_l2(q.pMO1 + e0 + pf);
+    k2_prefetch_l2(q.R + (q.pMX + e0 + pf)); k2_prefetch_l2(q.R + (q.pMO1 + e0 + pf));
     if (AFF) {
-      k2_prefetch_l2(q.pI1E + e0 + pf); k2_prefetch_l2(q.pD1E + e0 + pf);
-      if (HAS2) { if (MO2) k2_prefetch_l2(q.pMO2 + e0 + pf); k2_prefetch_l2(q.pI2E + e0 + pf); k2_prefetch_l2(q.pD2E + e0 + pf); }
+      k2_prefetch_l2(q.R + (q.pI1E + e0 + pf)); k2_prefetch_l2(q.R + (q.pD1E + e0 + pf));
+      if (HAS2) { if (MO2) k2_prefetch_l2(q.R + (q.pMO2 + e0 + pf)); k2_prefetch_l2(q.R + (q.pI2E + e0 + pf)); k2_prefetch_l2(q.R + (q.pD2E + e0 + pf)); }
     }
   }
   int32_t m1l, m1r;
@@ -217,11 +218,11 @@ __device__ __forceinline__ void k2_fast_chunk(unsigned char* __restrict__ btq, c
     k2_lds4(sb + K2_SR_MO1 * K2_SE, m1);
     m1l = sb[K2_SR_MO1 * K2_SE - 1]; m1r = sb[K2_SR_MO1 * K2_SE + 4];
   } else {
-    K2Vec<T>::load(q.pMX + e0, mx);
-    K2Vec<T>::load(q.pMO1 + e0, m1);
+    K2Vec<T>::load(q.R + (q.pMX + e0), mx);
+    K2Vec<T>::load(q.R + (q.pMO1 + e0), m1);
     m1l = __shfl_up_sync(FULL, m1[3], 1); m1r = __shfl_down_sync(FULL, m1[0], 1);
-    if (lane == 0) m1l = q.pMO1[e0 - 1u];
-    if (lane == 31) m1r = q.pMO1[e0 + 4u];
+    if (lane == 0) m1l = q.R[q.pMO1 + e0 - 1u];
+    if (lane == 31) m1r = q.R[q.pMO1 + e0 + 4u];
   }
   int32_t ins1[4], del1[4], ins2[4], del2[4];
   if (AFF) {
@@ -241,22 +242,22 @@ __device__ __forceinline__ void k2_fast_chunk(unsigned char* __restrict__ btq, c
         }
       }
     } else {
-      K2Vec<T>::load(q.pI1E + e0, a1);
-      K2Vec<T>::load(q.pD1E + e0, d1);
+      K2Vec<T>::load(q.R + (q.pI1E + e0), a1);
+      K2Vec<T>::load(q.R + (q.pD1E + e0), d1);
       a1l = __shfl_up_sync(FULL, a1[3], 1); d1r = __shfl_down_sync(FULL, d1[0], 1);
-      if (lane == 0) a1l = q.pI1E[e0 - 1u];
-      if (lane == 31) d1r = q.pD1E[e0 + 4u];
+      if (lane == 0) a1l = q.R[q.pI1E + e0 - 1u];
+      if (lane == 31) d1r = q.R[q.pD1E + e0 + 4u];
       if (HAS2) {
-        K2Vec<T>::load(q.pI2E + e0, a2);
-        K2Vec<T>::load(q.pD2E + e0, d2);
+        K2Vec<T>::load(q.R + (q.pI2E + e0), a2);
+        K2Vec<T>::load(q.R + (q.pD2E + e0), d2);
         a2l = __shfl_up_sync(FULL, a2[3], 1); d2r = __shfl_down_sync(FULL, d2[0], 1);
-        if (lane == 0) a2l = q.pI2E[e0 - 1u];
-        if (lane == 31) d2r = q.pD2E[e0 + 4u];
+        if (lane == 0) a2l = q.R[q.pI2E + e0 - 1u];
+        if (lane == 31) d2r = q.R[q.pD2E + e0 + 4u];
         if (MO2) {
-          K2Vec<T>::load(q.pMO2 + e0, m2);
+          K2Vec<T>::load(q.R + (q.pMO2 + e0), m2);
           m2l = __shfl_up_sync(FULL, m2[3], 1); m2r = __shfl_down_sync(FULL, m2[0], 1);
-          if (lane == 0) m2l = q.pMO2[e0 - 1u];
-          if (lane == 31) m2r = q.pMO2[e0 + 4u];
+          if (lane == 0) m2l = q.R[q.pMO2 + e0 - 1u];
+          if (lane == 31) m2r = q.R[q.pMO2 + e0 + 4u];
         } else {
           m2[0] = m2[1] = m2[2] = m2[3] = WNULL;
         }
@@ -304,9 +305,9 @@ __device__ __forceinline__ void k2_fast_chunk(unsigned char* __restrict__ btq, c
   // choice bytes and I/D rows do not depend on the extension: store them first
   *reinterpret_cast<uint32_t*>(btq + e0) = ch[0] | (ch[1] << 8) | (ch[2] << 16) | (ch[3] << 24);
   if (AFF) {
-    K2Vec<T>::store(q.oI1 + e0, ins1);
-    K2Vec<T>::store(q.oD1 + e0, del1);
-    if (HAS2) { K2Vec<T>::store(q.oI2 + e0, ins2); K2Vec<T>::store(q.oD2 + e0, del2); }
+    K2Vec<T>::store(q.R + (q.oI1 + e0), ins1);
+    K2Vec<T>::store(q.R + (q.oD1 + e0), del1);
+    if (HAS2) { K2Vec<T>::store(q.R + (q.oI2 + e0), ins2); K2Vec<T>::store(q.R + (q.oD2 + e0), del2); }
   }
   // bounds + first 8-base window of the four cells (independent chains)
   uint32_t xw[4];
@@ -341,12 +342,12 @@ __device__ __forceinline__ void k2_fast_chunk(unsigned char* __restrict__ btq, c
       }
     }
   }
-  K2Vec<T>::store(q.oM + e0, best);
+  K2Vec<T>::store(q.R + (q.oM + e0), best);
 }
 
 template <bool AFF, typename T>
 #ifndef K2_LB_T
-#define K2_LB_T 512
+#define K2_LB_T 384
 #define K2_LB_B 1
 #endif
 __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
@@ -541,9 +542,9 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
         }
       };
       K2Rows<T> rows;
-      rows.pMX = R + qMX; rows.pMO1 = R + qMO1; rows.pMO2 = R + qMO2; rows.pI1E = R + qI1E; rows.pD1E = R + qD1E;
-      rows.pI2E = R + qI2E; rows.pD2E = R + qD2E;
-      rows.oM = rings + wM; rows.oI1 = rings + wI1; rows.oD1 = rings + wD1; rows.oI2 = rings + wI2; rows.oD2 = rings + wD2;
+      rows.R = rings;
+      rows.pMX = qMX; rows.pMO1 = qMO1; rows.pMO2 = qMO2; rows.pI1E = qI1E; rows.pD1E = qD1E; rows.pI2E = qI2E; rows.pD2E = qD2E;
+      rows.oM = wM; rows.oI1 = wI1; rows.oD1 = wD1; rows.oI2 = wI2; rows.oD2 = wD2;
       unsigned char* btq = btrow - ((size_t)g_lo << 2);  // indexed by the element offset e = k + kbase
       const int flo = max(ilo, lo), fhi = min(ihi, hi);
       const int flo_b = max(ilo_b, lo), fhi_b = min(ihi_b, hi);

@@ -463,7 +463,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     std::vector<Job> jobs;
     // small pairs: one 128-thread CTA each
     if (k2l_begin > k2s_begin) jobs.push_back(Job{std::vector<uint32_t>(c->h_order.begin() + k2s_begin, c->h_order.begin() + k2l_begin), 128, 1});
-    // large pairs: 512-thread CTAs; a pair whose estimated work exceeds the balanced per-SM share is spread over a
+    // large pairs: 384-thread CTAs; a pair whose estimated work exceeds the balanced per-SM share is spread over a
     // thread-block cluster of 2/4/8 CTAs so that the heaviest alignment does not set the batch time
     if (n > k2l_begin) {
       const size_t nl = n - k2l_begin;
@@ -489,7 +489,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       for (int ci = 3; ci >= 0; --ci) {
         if (tmp[ci].empty()) continue;
         std::stable_sort(tmp[ci].begin(), tmp[ci].end(), [](const std::pair<double, uint32_t>& x, const std::pair<double, uint32_t>& y) { return x.first > y.first; });
-        Job j; j.threads = 512; j.C = 1 << ci;
+        Job j; j.threads = K2_LB_T; j.C = 1 << ci;
         if (const char* e = getenv("SFC_K2_THREADS")) j.threads = std::max(64, std::min(K2_LB_T, atoi(e)));  // experiment knob
         for (auto& t : tmp[ci]) j.list.push_back(t.second);
         jobs.push_back(std::move(j));
@@ -666,12 +666,12 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       }
       divisor *= 4;
       Plan pl;
-      if ((rc = plan_job(retry, 512, 1, avail, divisor, &pl))) return rc;
+      if ((rc = plan_job(retry, K2_LB_T, 1, avail, divisor, &pl))) return rc;
       if ((rc = ensure(c, c->d_ws, pl.slab * pl.n_cl))) return rc;
       cur = retry;
       CU(cudaMemcpyAsync((uint32_t*)c->d_order.p + k2s_begin, retry.data(), retry.size() * 4, cudaMemcpyHostToDevice, c->stream));
       CU(cudaMemsetAsync(misc + 8, 0, 4, c->stream));
-      if ((rc = launch_job((const uint32_t*)c->d_order.p + k2s_begin, retry.size(), 512, 1, pl, (unsigned char*)c->d_ws.p, misc + 8, c->stream))) return rc;
+      if ((rc = launch_job((const uint32_t*)c->d_order.p + k2s_begin, retry.size(), K2_LB_T, 1, pl, (unsigned char*)c->d_ws.p, misc + 8, c->stream))) return rc;
       if (pl.n_cl == 1 && pl.slab >= avail - 4096 && !pool_short) divisor = 1 << 20;  // last resort was tried
     }
   }

@@ -1,12 +1,10 @@
 #!/bin/bash
-# A/B runs of K2 variants (writes gpurun_out/ab_k2.log)
 mkdir -p gpurun_out
 {
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-for st in 2 3; do
-  echo "== stages $st"; SFC_K2_STAGES=$st python tools/bench_summary.py --workload config2 --no-cpu-baseline
+for t in 256 320 448; do
+echo "== ${t}x1"; SFC_SO_PATH=build/lib_${t}_1.so SFC_K2_THREADS=$t python tools/bench_summary.py --workload config2 --no-cpu-baseline
+echo "== ${t}x1 config3"; SFC_SO_PATH=build/lib_${t}_1.so SFC_K2_THREADS=$t python tools/bench_summary.py --workload config3 --no-cpu-baseline
 done
-echo "== stages 2 config3"; python tools/bench_summary.py --workload config3 --no-cpu-baseline
-echo "== prof"; SFC_K2_PROF=1 python bench.py --workload config2 --no-cpu-baseline --steps 2 --warmup 1 2>&1 | grep "k2 prof" | tail -1
+echo "== 384x1 stages 3"; SFC_K2_STAGES=3 SFC_SO_PATH=build/lib_384_1.so SFC_K2_THREADS=384 python tools/bench_summary.py --workload config2 --no-cpu-baseline
 } > gpurun_out/ab_k2.log 2>&1
 cat gpurun_out/ab_k2.log
