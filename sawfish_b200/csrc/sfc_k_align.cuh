@@ -32,6 +32,12 @@ enum { K2_SEL_X = 0, K2_SEL_I1 = 1, K2_SEL_I2 = 2, K2_SEL_D1 = 3, K2_SEL_D2 = 4 
 constexpr uint32_t K2_BIT_I1E = 0x08, K2_BIT_I2E = 0x10, K2_BIT_D1E = 0x20, K2_BIT_D2E = 0x40;
 enum { K2_E_X = 0, K2_E_IO = 1, K2_E_IE = 2, K2_E_DO = 3, K2_E_DE = 4 };  // backward edit codes
 enum { K2_C_M = 0, K2_C_I1 = 1, K2_C_D1 = 2, K2_C_I2 = 3, K2_C_D2 = 4 };
+// per-score plan in shared memory (ints from misc + 4), see k2_align
+enum { K2_D_S = 0, K2_D_STATUS, K2_D_LO, K2_D_HI, K2_D_HAS2, K2_D_G1A, K2_D_G1B, K2_D_G2A, K2_D_G2B, K2_D_M2A, K2_D_M2B,
+       K2_D_Q = 12 /* 12 row offsets */, K2_D_RLO = 24 /* 7 */, K2_D_RCNT = 31 /* 7 */, K2_D_OSLOT = 38 /* 5 */,
+       K2_D_CLO = 43 /* 5: raw (untrimmed) range of each output component, */, K2_D_CHI = 48 /* 5 */,
+       K2_D_BT = 58 /* index from misc: two 64-bit counters */, K2_D_TAB = 64 /* index from misc: plan table [32 lanes][5] */ };
+constexpr int K2_MISC_BYTES = 1024;  // misc area behind the range metadata: pair index, terminating diagonal, plan
 
 struct K2Params {
   const DevPair* pairs;
@@ -368,18 +374,18 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
   constexpr bool CAN_STAGE = sizeof(T) == 4;
   const int NR = AFF ? (int)K2_SR_N : 2;  // staged rows per chunk
   const int S = CAN_STAGE ? P.stages : 0;
-  int32_t* wstg = reinterpret_cast<int32_t*>(k2_smem + (((size_t)P.win_cap * 8 + (size_t)nslots * 8 + 64 + 15) & ~(size_t)15)) +
+  int32_t* wstg = reinterpret_cast<int32_t*>(k2_smem + (((size_t)P.win_cap * 8 + (size_t)nslots * 8 + K2_MISC_BYTES + 15) & ~(size_t)15)) +
                   (size_t)(threadIdx.x >> 5) * S * NR * K2_SE;
   unsigned char* slab = P.slabs + (size_t)(blockIdx.x / C) * P.slab_bytes;
   int* misc0 = C > 1 ? cluster.map_shared_rank(misc, 0) : misc;  // rank 0's copy: work index + terminating diagonal
   unsigned long long cells_acc = 0;
-  long long t_cells = 0, t_sync = 0, t_bt = 0, t_setup = 0, t_mark = clock64();
+  long long t_cells = 0, t_sync = 0, t_bt = 0, t_setup = 0, t_trim = 0, t_plan = 0, t_mark = clock64();
 #define K2_TICK(acc) do { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; } while (0)
 
   for (;;) {
     csync();
     K2_TICK(t_bt);
-    if (crank == 0 && tid == 0) { misc[0] = (int)atomicAdd(P.counter, 1u); misc[1] = INT_MAX; }
+    if (crank == 0 && tid == 0) { misc[0] = (int)atomicAdd(P.counter, 1u); misc[1] = misc[2] = INT_MAX; }
     csync();
     const uint32_t wi = (uint32_t)misc0[0];
     if (wi >= P.n) { csync(); break; }  // no CTA may exit while a peer can still read its shared memory
@@ -414,7 +420,6 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
     uint32_t* tmp_f = tmp_b + (tmp_bytes >> 2);
     unsigned char* bt = slab + fixed;
     const unsigned long long bt_cap = P.slab_bytes - fixed;
-    unsigned long long bt_used = 0;
     {
       const uint32_t* gp = P.nib + pr.p_woff;
       const uint32_t* gt = P.nib + pr.t_woff;
@@ -423,111 +428,137 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
     }
     __syncthreads();
 
-    // slot bases per component (row index == slot index); all row offsets are 32-bit element offsets into rings
+    // ---- per-score plan ----
+    // Ring slots, source ranges, the wavefront's own range, the chunk classification and the choice-row offset of a
+    // score are computed ONCE per CTA by warp 0 (lane r handles ring row r) between the two barriers of the previous
+    // score and published in shared memory (D); the other warps only read them.
     const int sbM = 0, sbI1 = P.nM, sbD1 = P.nM + P.nG1, sbI2 = P.nM + 2 * P.nG1, sbD2 = P.nM + 2 * P.nG1 + P.nG2;
-    // slot (== ring row) of component c at score `sc` <= s_now: (s_now mod depth) is kept incrementally in cur* because
-    // an integer modulo by a run-time value costs ~25 instructions and a score step needs a dozen of them
-    int curM = 0, curG1 = 0, curG2 = 0;
-    auto slot_of = [&](int c, int sc, int s_now) -> int {
-      const int back = s_now - sc;  // 0 <= back < depth for every row that is still in the ring
-      if (c == K2_C_M) { const int v = curM - min(back, P.nM - 1); return sbM + v + (v < 0 ? P.nM : 0); }
-      if (c == K2_C_I1 || c == K2_C_D1) {
-        const int v = curG1 - min(back, P.nG1 - 1);
-        return (c == K2_C_I1 ? sbI1 : sbD1) + v + (v < 0 ? P.nG1 : 0);
+    int* D = misc + 4;
+    unsigned long long* D64 = reinterpret_cast<unsigned long long*>(misc + K2_D_BT);  // [0] choice bytes used, [1] cells
+    // cluster-wide min of terminating diagonals (rank 0's shared memory, reset at pair fetch); two slots used alternately
+    // because only barrier 1 is cluster-wide: a CTA may start the next score while a peer still reads this one's slot
+    const int ncomp = AFF ? 5 : 1;
+    auto plan = [&](int s_from) {  // warp 0: find the next existing score >= s_from and publish its plan
+      // per-lane row constants from the table built at pair start: ring depth, first slot, score distance, range shifts
+      int* tab = misc + K2_D_TAB + lane * 5;
+      const int back = tab[0], sbase = tab[1], depth = tab[2], dpk = tab[3];
+      int rel = tab[4];  // (sN - back) mod depth, kept incrementally (an integer modulo costs ~40 dependent instructions)
+      const int dl = (int)(signed char)(dpk & 0xFF), dh = (int)(signed char)((dpk >> 8) & 0xFF);
+      const int il = (int)(signed char)((dpk >> 16) & 0xFF), ih = (int)(signed char)((dpk >> 24) & 0xFF);
+      const bool is_src = lane < (AFF ? 7 : 2), is_out = lane >= 7 && lane < 7 + ncomp;
+      unsigned long long bt_used = D64[0];
+      for (int sN = s_from;; ++sN) {
+        if (sN > S_cap) { if (lane == 0) D[K2_D_STATUS] = -7; break; }
+        const int sc = sN - back;
+        const int slot = sbase + rel;
+        rel = rel + 1 == depth ? 0 : rel + 1;
+        int rlo = 1, rhi = -1;
+        if (is_src && sc >= 0 && sN > 0) { rlo = meta[2 * slot]; rhi = meta[2 * slot + 1]; }
+        const bool any = rlo <= rhi;
+        const unsigned anym = __ballot_sync(FULL, any);
+        int lo = warp_min(any ? rlo + dl : INT_MAX), hi = warp_max(any ? rhi + dh : INT_MIN);
+        if (sN == 0) { lo = -pr.pbf; hi = pr.tbf; }
+        if (lo > hi) {  // wavefront sN does not exist: its rows are empty
+          if (is_out) { meta[2 * slot] = 1; meta[2 * slot + 1] = -1; }
+          __syncwarp();
+          continue;
+        }
+        const bool has2 = AFF && (anym & 0x70u) != 0u;
+        // interior 1: every read of every existing-piece source in range; interior 2: everything but M[s-o2'-e2']
+        const unsigned set1 = has2 ? 0x7Fu : (AFF ? 0x0Fu : 0x03u), set2 = 0x3Fu;
+        const bool in1 = (set1 >> lane) & 1u, in2 = (set2 >> lane) & 1u;
+        int ilo = warp_max(in1 ? rlo + il : INT_MIN), ihi = warp_min(in1 ? rhi + ih : INT_MAX);
+        int ilo_b = warp_max(in2 ? rlo + il : INT_MIN), ihi_b = warp_min(in2 ? rhi + ih : INT_MAX);
+        if ((anym & set1) != set1 || sN == 0) { ilo = 1; ihi = 0; }
+        if (!(AFF && has2) || (anym & set2) != set2 || sN == 0) { ilo_b = 1; ihi_b = 0; }
+        const int flo = max(ilo, lo), fhi = min(ihi, hi), flo_b = max(ilo_b, lo), fhi_b = min(ihi_b, hi);
+        const int g_lo = (lo + kbase) >> 2, g_hi = (hi + kbase) >> 2;
+        const unsigned long long bt_row_bytes = 4ull * (unsigned long long)(g_hi - g_lo + 1);
+        if (bt_used + bt_row_bytes > bt_cap) { if (lane == 0) D[K2_D_STATUS] = -6; break; }
+        const int m2lo = __shfl_sync(FULL, rlo, K2_SR_MO2), m2hi = __shfl_sync(FULL, rhi, K2_SR_MO2);
+        if (lane < 12) D[K2_D_Q + lane] = (int)((unsigned)slot * (unsigned)Wp);
+        if (is_out) D[K2_D_OSLOT + lane - 7] = slot;
+        if (lane < 7) { D[K2_D_RLO + lane] = rlo; D[K2_D_RCNT + lane] = max(rhi - rlo + 1, 0); }
+        {  // raw (untrimmed) diagonal range of each output component: where its two sources can be non-null
+          const int mo1lo = __shfl_sync(FULL, rlo, K2_SR_MO1), mo1hi = __shfl_sync(FULL, rhi, K2_SR_MO1);
+          // lane c+1 (c = 1..4 -> rows I1E, D1E, I2E, D2E hold the extension source of component c)
+          const bool g2 = lane == K2_SR_I2E || lane == K2_SR_D2E;
+          const int olo = g2 ? m2lo : mo1lo, ohi = g2 ? m2hi : mo1hi;  // the gap-open source M row
+          const bool oany = olo <= ohi;
+          int clo = any ? (oany ? min(rlo, olo) : rlo) : (oany ? olo : 1), chi = any ? (oany ? max(rhi, ohi) : rhi) : (oany ? ohi : -1);
+          if (any || oany) { clo += dl; chi += dl; }  // insertions read k-1 (range shifts by +1), deletions k+1 (-1); dl == dh for these rows
+          if (lane >= K2_SR_I1E && lane <= K2_SR_D2E) { D[K2_D_CLO + lane - 1] = max(clo, lo); D[K2_D_CHI + lane - 1] = min(chi, hi); }
+          if (lane == 0) { D[K2_D_CLO] = lo; D[K2_D_CHI] = hi; }
+        }
+        if (lane == 0) {
+          D[K2_D_S] = sN; D[K2_D_LO] = lo; D[K2_D_HI] = hi; D[K2_D_HAS2] = has2;
+          // chunk kinds as ranges of the chunk's first group gb (chunk diagonals 4*gb - kbase .. + 127)
+          const bool e1 = flo + 127 > fhi, e2 = flo_b + 127 > fhi_b;
+          D[K2_D_G1A] = e1 ? INT_MAX : (flo + kbase + 3) >> 2;  D[K2_D_G1B] = e1 ? INT_MIN : (fhi - 127 + kbase) >> 2;
+          D[K2_D_G2A] = e2 ? INT_MAX : (flo_b + kbase + 3) >> 2; D[K2_D_G2B] = e2 ? INT_MIN : (fhi_b - 127 + kbase) >> 2;
+          const bool m2any = m2lo <= m2hi;  // kind 2 must be clear of M[s-o2'-e2'] (gap-open-2 candidates all null)
+          D[K2_D_M2A] = m2any ? (m2lo + kbase - 129) >> 2 : INT_MAX;  // gb <= M2A: chunk entirely left of it
+          D[K2_D_M2B] = m2any ? ((m2hi + kbase + 1) >> 2) + 1 : INT_MIN;  // gb >= M2B: entirely right of it
+        }
+        break;
       }
-      const int v = curG2 - min(back, P.nG2 - 1);
-      return (c == K2_C_I2 ? sbI2 : sbD2) + v + (v < 0 ? P.nG2 : 0);
+      tab[4] = rel;
+      __syncwarp();
     };
-    auto get = [&](int c, int sc, int s_now) -> K2Range {
-      K2Range r; r.lo = 1; r.hi = -1;
-      if (sc < 0) return r;
-      const int sl = slot_of(c, sc, s_now);
-      r.lo = meta[2 * sl]; r.hi = meta[2 * sl + 1];
-      return r;
-    };
-    int* term_slot = misc0 + 1;  // cluster-wide min of terminating diagonals (reset at pair fetch)
+    if (warp == 0) {
+      if (lane == 0) { D[K2_D_STATUS] = 0; D64[0] = 0; D64[1] = 0; }
+      {  // plan table: rows 0..6 sources in staging order (MX, MO1, I1E, D1E, I2E, D2E, MO2); rows 7..11 outputs (M, I1, D1, I2, D2)
+        int comp = K2_C_M, back = 0, dl = 0, dh = 0, il = 0, ih = 0;
+        switch (lane) {
+          case 0: back = P.x; break;
+          case 1: back = AFF ? P.o1 + P.e1 : P.e1; dl = -1; dh = 1; il = 1; ih = -1; break;
+          case 2: comp = K2_C_I1; back = P.e1; dl = dh = 1; il = ih = 1; break;
+          case 3: comp = K2_C_D1; back = P.e1; dl = dh = -1; il = ih = -1; break;
+          case 4: comp = K2_C_I2; back = P.e2; dl = dh = 1; il = ih = 1; break;
+          case 5: comp = K2_C_D2; back = P.e2; dl = dh = -1; il = ih = -1; break;
+          case 6: back = P.o2 + P.e2; dl = -1; dh = 1; il = 1; ih = -1; break;
+          case 8: comp = K2_C_I1; break;
+          case 9: comp = K2_C_D1; break;
+          case 10: comp = K2_C_I2; break;
+          case 11: comp = K2_C_D2; break;
+          default: break;
+        }
+        const int depth = max(comp == K2_C_M ? P.nM : (comp == K2_C_I1 || comp == K2_C_D1) ? P.nG1 : P.nG2, 1);
+        const int sbase = comp == K2_C_M ? sbM : comp == K2_C_I1 ? sbI1 : comp == K2_C_D1 ? sbD1 : comp == K2_C_I2 ? sbI2 : sbD2;
+        int* tab = misc + K2_D_TAB + lane * 5;
+        tab[0] = back; tab[1] = sbase; tab[2] = depth;
+        tab[3] = (dl & 0xFF) | ((dh & 0xFF) << 8) | ((il & 0xFF) << 16) | ((ih & 0xFF) << 24);
+        tab[4] = (depth - back % depth) % depth;  // (0 - back) mod depth
+      }
+      __syncwarp();
+      plan(0);
+    }
 
     int s = 0, end_k = 0;
     bool done = false;
     K2_TICK(t_setup);
-    for (;; ++s, curM = (curM + 1 == P.nM ? 0 : curM + 1), curG1 = (curG1 + 1 == P.nG1 ? 0 : curG1 + 1),
-                curG2 = (curG2 + 1 == P.nG2 ? 0 : curG2 + 1)) {
-      if (s > S_cap) { res_status = -7; break; }
-      // ---- source wavefronts ----
-      const int s_mx = s - P.x;
-      const int s_o1 = AFF ? s - P.o1 - P.e1 : s - P.e1;
-      const int s_o2 = s - P.o2 - P.e2, s_e1 = s - P.e1, s_e2 = s - P.e2;
-      K2Range MX, MO1, MO2, I1E, D1E, I2E, D2E;
-      MX.lo = MO1.lo = MO2.lo = I1E.lo = D1E.lo = I2E.lo = D2E.lo = 1;
-      MX.hi = MO1.hi = MO2.hi = I1E.hi = D1E.hi = I2E.hi = D2E.hi = -1;
-      int lo = INT_MAX, hi = INT_MIN;
-      if (s == 0) { lo = -pr.pbf; hi = pr.tbf; }
-      else {
-        MX = get(K2_C_M, s_mx, s); MO1 = get(K2_C_M, s_o1, s);
-        if (MX.any()) { lo = min(lo, MX.lo); hi = max(hi, MX.hi); }
-        if (MO1.any()) { lo = min(lo, MO1.lo - 1); hi = max(hi, MO1.hi + 1); }
-        if (AFF) {
-          MO2 = get(K2_C_M, s_o2, s); I1E = get(K2_C_I1, s_e1, s); D1E = get(K2_C_D1, s_e1, s);
-          I2E = get(K2_C_I2, s_e2, s); D2E = get(K2_C_D2, s_e2, s);
-          if (MO2.any()) { lo = min(lo, MO2.lo - 1); hi = max(hi, MO2.hi + 1); }
-          if (I1E.any()) { lo = min(lo, I1E.lo + 1); hi = max(hi, I1E.hi + 1); }
-          if (D1E.any()) { lo = min(lo, D1E.lo - 1); hi = max(hi, D1E.hi - 1); }
-          if (I2E.any()) { lo = min(lo, I2E.lo + 1); hi = max(hi, I2E.hi + 1); }
-          if (D2E.any()) { lo = min(lo, D2E.lo - 1); hi = max(hi, D2E.hi - 1); }
-        }
-      }
-      if (lo > hi) {  // wavefront s does not exist
-        if (tid == 0) {  // every CTA marks its own copy
-          for (int c = 0; c < (AFF ? 5 : 1); ++c) { meta[2 * slot_of(c, s, s)] = 1; meta[2 * slot_of(c, s, s) + 1] = -1; }
-        }
-        __syncthreads();
-        continue;
-      }
-      const int width = hi - lo + 1;
-      // choice bytes are stored per 4-diagonal group: row s covers diagonals [4*g_lo - kbase, 4*g_hi + 3 - kbase]
-      const unsigned long long bt_row_bytes = 4ull * (unsigned long long)((((hi + kbase) >> 2) - ((lo + kbase) >> 2)) + 1);
-      if (bt_used + bt_row_bytes > bt_cap) { res_status = -6; break; }
-      const bool has2 = AFF && (MO2.any() || I2E.any() || D2E.any());
-      // interior where every read of every (existing-piece) source is in range
-      int ilo, ihi;
-      {
-        bool ok = MX.any() && MO1.any();
-        ilo = max(MX.lo, MO1.lo + 1); ihi = min(MX.hi, MO1.hi - 1);
-        if (AFF) {
-          ok = ok && I1E.any() && D1E.any();
-          ilo = max(ilo, max(I1E.lo + 1, D1E.lo - 1)); ihi = min(ihi, min(I1E.hi + 1, D1E.hi - 1));
-          if (has2) {
-            ok = ok && MO2.any() && I2E.any() && D2E.any();
-            ilo = max(ilo, max(MO2.lo + 1, max(I2E.lo + 1, D2E.lo - 1)));
-            ihi = min(ihi, min(MO2.hi - 1, min(I2E.hi + 1, D2E.hi - 1)));
-          }
-        }
-        if (!ok || s == 0) { ilo = 1; ihi = 0; }
-      }
-      // second interior: everything but M[s-o2'-e2'] in range (that row is ~120 diagonals narrower on both sides)
-      int ilo_b = 1, ihi_b = 0;
-      if (AFF && has2 && s > 0 && MX.any() && MO1.any() && I1E.any() && D1E.any() && I2E.any() && D2E.any()) {
-        ilo_b = max(max(MX.lo, MO1.lo + 1), max(max(I1E.lo + 1, D1E.lo - 1), max(I2E.lo + 1, D2E.lo - 1)));
-        ihi_b = min(min(MX.hi, MO1.hi - 1), min(min(I1E.hi + 1, D1E.hi - 1), min(I2E.hi + 1, D2E.hi - 1)));
-      }
+    for (int it = 0;; ++it) {
+      int* term_slot = misc0 + 1 + (it & 1);
+      __syncthreads();  // barrier 2: plan of the next score (and the trimmed ranges behind it) visible; CTA-local
+      K2_TICK(t_sync);
+      { const int st = D[K2_D_STATUS]; if (st != 0) { res_status = st; break; } }
+      s = D[K2_D_S];
+      const int lo = D[K2_D_LO], hi = D[K2_D_HI];
+      const bool has2 = D[K2_D_HAS2] != 0;
+      const int G1A = D[K2_D_G1A], G1B = D[K2_D_G1B], G2A = D[K2_D_G2A], G2B = D[K2_D_G2B], M2A = D[K2_D_M2A], M2B = D[K2_D_M2B];
+      const unsigned long long bt_used = D64[0];
       const T* __restrict__ R = rings;
-      // unsigned element offsets of the row starts (row r, diagonal k lives at r*Wp + kbase + k >= 0)
-      const unsigned uWp = (unsigned)Wp;
-      const unsigned qMX = (unsigned)slot_of(K2_C_M, max(s_mx, 0), s) * uWp, qMO1 = (unsigned)slot_of(K2_C_M, max(s_o1, 0), s) * uWp;
-      const unsigned qMO2 = (unsigned)slot_of(K2_C_M, max(s_o2, 0), s) * uWp;
-      const unsigned qI1E = (unsigned)slot_of(K2_C_I1, max(s_e1, 0), s) * uWp, qD1E = (unsigned)slot_of(K2_C_D1, max(s_e1, 0), s) * uWp;
-      const unsigned qI2E = (unsigned)slot_of(K2_C_I2, max(s_e2, 0), s) * uWp, qD2E = (unsigned)slot_of(K2_C_D2, max(s_e2, 0), s) * uWp;
-      const unsigned wM = (unsigned)slot_of(K2_C_M, s, s) * uWp, wI1 = (unsigned)slot_of(K2_C_I1, s, s) * uWp, wD1 = (unsigned)slot_of(K2_C_D1, s, s) * uWp;
-      const unsigned wI2 = (unsigned)slot_of(K2_C_I2, s, s) * uWp, wD2 = (unsigned)slot_of(K2_C_D2, s, s) * uWp;
+      const unsigned qMX = (unsigned)D[K2_D_Q + 0], qMO1 = (unsigned)D[K2_D_Q + 1], qI1E = (unsigned)D[K2_D_Q + 2], qD1E = (unsigned)D[K2_D_Q + 3];
+      const unsigned qI2E = (unsigned)D[K2_D_Q + 4], qD2E = (unsigned)D[K2_D_Q + 5], qMO2 = (unsigned)D[K2_D_Q + 6];
+      const unsigned wM = (unsigned)D[K2_D_Q + 7], wI1 = (unsigned)D[K2_D_Q + 8], wD1 = (unsigned)D[K2_D_Q + 9];
+      const unsigned wI2 = (unsigned)D[K2_D_Q + 10], wD2 = (unsigned)D[K2_D_Q + 11];
       unsigned char* btrow = bt + bt_used;  // byte index = (k + kbase) - 4*g_lo
-      const int cMX = MX.cnt(), cMO1 = MO1.cnt(), cMO2 = MO2.cnt(), cI1E = I1E.cnt(), cD1E = D1E.cnt(),
-                cI2E = I2E.cnt(), cD2E = D2E.cnt();
       int term_k = INT_MAX;
 
-      // ---- cell loop: each thread owns a group of 4 consecutive diagonals (one 8/16-byte vector per ring row),
-      // a warp a chunk of 128; the k-1 / k+1 neighbours come from the adjacent lanes by shuffle ----
+      // ---- cell loop: each thread owns a group of 4 consecutive diagonals (one 16-byte vector per ring row),
+      // a warp a chunk of 128 ----
       const int g_lo = (lo + kbase) >> 2, g_hi = (hi + kbase) >> 2;
-      auto in_rng = [](int k, const K2Range& r, int cnt) -> bool { return (unsigned)(k - r.lo) < (unsigned)cnt; };
+      auto in_rng = [&](int k, int row) -> bool { return (unsigned)(k - D[K2_D_RLO + row]) < (unsigned)D[K2_D_RCNT + row]; };
       // vector of a row at my group, plus the element just left / right of it (from the neighbouring lanes)
       auto load_row = [&](unsigned q, unsigned e0, bool ok, bool last_group, bool want_l, bool want_r, int32_t (&v)[4], int32_t& left, int32_t& right) {
         v[0] = v[1] = v[2] = v[3] = WNULL;
@@ -546,13 +577,10 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
       rows.pMX = qMX; rows.pMO1 = qMO1; rows.pMO2 = qMO2; rows.pI1E = qI1E; rows.pD1E = qD1E; rows.pI2E = qI2E; rows.pD2E = qD2E;
       rows.oM = wM; rows.oI1 = wI1; rows.oD1 = wD1; rows.oI2 = wI2; rows.oD2 = wD2;
       unsigned char* btq = btrow - ((size_t)g_lo << 2);  // indexed by the element offset e = k + kbase
-      const int flo = max(ilo, lo), fhi = min(ihi, hi);
-      const int flo_b = max(ilo_b, lo), fhi_b = min(ihi_b, hi);
       // 1: interior of every source; 2: interior of everything but M[s-o2'-e2'] and clear of it; 0: boundary (guarded)
       auto kind_of = [&](int gb) -> int {
-        const int kA = (gb << 2) - kbase, kB = kA + 127;
-        if (s > 0 && kA >= flo && kB <= fhi) return 1;
-        if (AFF && kA >= flo_b && kB <= fhi_b && (!MO2.any() || kB + 1 < MO2.lo || kA - 1 > MO2.hi)) return 2;
+        if (gb >= G1A && gb <= G1B) return 1;
+        if (AFF && gb >= G2A && gb <= G2B && (gb <= M2A || gb >= M2B)) return 2;
         return 0;
       };
       const int gstep = C * NW * 32;
@@ -610,8 +638,6 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) { const int k = k0 + j; if (k >= lo && k <= hi) best[j] = max(k, 0); }
         } else {
-          const int kA = (gb << 2) - kbase, kB = kA + 127;
-          const bool fast = kA >= max(ilo, lo) && kB <= min(ihi, hi);
           const bool lastg = (g == g_hi);
           int32_t mx[4], m1[4], m1l, m1r, a1[4], a1l, d1[4], d1r, dummy = 0;
           int32_t m2[4], m2l = WNULL, m2r = WNULL, a2[4], a2l = WNULL, d2[4], d2r = WNULL;
@@ -659,18 +685,18 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
             int32_t i1e = j == 0 ? a1l : a1[j > 0 ? j - 1 : 0], d1e = j == 3 ? d1r : d1[j < 3 ? j + 1 : 3];
             int32_t i2o = j == 0 ? m2l : m2[j > 0 ? j - 1 : 0], d2o = j == 3 ? m2r : m2[j < 3 ? j + 1 : 3];
             int32_t i2e = j == 0 ? a2l : a2[j > 0 ? j - 1 : 0], d2e = j == 3 ? d2r : d2[j < 3 ? j + 1 : 3];
-            if (!fast) {  // boundary chunk: every read is checked against its source wavefront's live range
+            {  // boundary chunk: every read is checked against its source wavefront's live range
               const bool act = k >= lo && k <= hi;
-              vmx = (act && in_rng(k, MX, cMX)) ? vmx : WNULL;
-              i1o = (act && in_rng(k - 1, MO1, cMO1)) ? i1o : WNULL;
-              d1o = (act && in_rng(k + 1, MO1, cMO1)) ? d1o : WNULL;
+              vmx = (act && in_rng(k, K2_SR_MX)) ? vmx : WNULL;
+              i1o = (act && in_rng(k - 1, K2_SR_MO1)) ? i1o : WNULL;
+              d1o = (act && in_rng(k + 1, K2_SR_MO1)) ? d1o : WNULL;
               if (AFF) {
-                i1e = (act && in_rng(k - 1, I1E, cI1E)) ? i1e : WNULL;
-                d1e = (act && in_rng(k + 1, D1E, cD1E)) ? d1e : WNULL;
-                i2o = (act && in_rng(k - 1, MO2, cMO2)) ? i2o : WNULL;
-                d2o = (act && in_rng(k + 1, MO2, cMO2)) ? d2o : WNULL;
-                i2e = (act && in_rng(k - 1, I2E, cI2E)) ? i2e : WNULL;
-                d2e = (act && in_rng(k + 1, D2E, cD2E)) ? d2e : WNULL;
+                i1e = (act && in_rng(k - 1, K2_SR_I1E)) ? i1e : WNULL;
+                d1e = (act && in_rng(k + 1, K2_SR_D1E)) ? d1e : WNULL;
+                i2o = (act && in_rng(k - 1, K2_SR_MO2)) ? i2o : WNULL;
+                d2o = (act && in_rng(k + 1, K2_SR_MO2)) ? d2o : WNULL;
+                i2e = (act && in_rng(k - 1, K2_SR_I2E)) ? i2e : WNULL;
+                d2e = (act && in_rng(k + 1, K2_SR_D2E)) ? d2e : WNULL;
               }
             }
             const int32_t mis = vmx + 1;
@@ -758,64 +784,78 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
         }
       }
       K2_TICK(t_cells);
-      // ---- barrier 1: rows of score s complete; did any diagonal terminate? ----
+      // ---- barrier 1: rows of score s complete (cluster-wide); did any diagonal terminate? ----
       term_k = warp_min(term_k);
       if (term_k != INT_MAX && lane == 0) atomicMin(term_slot, term_k);
       csync();
       const int tk = *term_slot;
       if (tk != INT_MAX) {
         end_k = tk; done = true;
-        if (crank == 0 && tid == 0) { rowoff[s] = bt_used; rowlo[s] = (((lo + kbase) >> 2) << 2) - kbase; cells_acc += (unsigned long long)width; }
+        if (crank == 0 && tid == 0) { rowoff[s] = bt_used; rowlo[s] = (g_lo << 2) - kbase; D64[1] += (unsigned long long)(hi - lo + 1); }
         break;
       }
-      // ---- trim every component to its first / last in-matrix diagonal (metadata only) ----
-      {
-        const int ncomp = AFF ? 5 : 1;
-        for (int task = crank * NW + warp; task < 2 * ncomp; task += C * NW) {
-          const int c = task >> 1, side = task & 1;
-          const int sl = slot_of(c, s, s);
-          int found = side ? -1 : 1;  // empty encoding: lo = 1, hi = -1
-          if (c == K2_C_M || s > 0) {
-            if ((c == K2_C_I2 || c == K2_C_D2) && !has2) {
-              // piece-2 wavefronts do not exist yet
+      // ---- warp 0 (of every CTA of a cluster, redundantly): trim the rows of score s, then plan the next score ----
+      K2_TICK(t_sync);
+      if (warp == 0) {
+        // trim every component of score s to its first / last in-matrix diagonal (metadata only).  All ten scans
+        // (5 components x 2 sides) probe their first three diagonals with ONE load: lane 3t+j reads diagonal j of scan t,
+        // starting from the component's raw range.  A scan with no hit there (rare) continues 32 diagonals at a time.
+        {
+          const int t = lane / 3, j = lane - 3 * t, c = min(t >> 1, 4), side = t & 1;
+          const bool en = t < 2 * ncomp && (c == K2_C_M || s > 0) && !((c == K2_C_I2 || c == K2_C_D2) && !has2);
+          const int clo = en ? D[K2_D_CLO + c] : 1, chi = en ? D[K2_D_CHI + c] : -1;
+          const unsigned q = (unsigned)D[K2_D_Q + 7 + c] + (unsigned)kbase;
+          const int k = side ? chi - j : clo + j;
+          const bool ok = k >= clo && k <= chi;
+          const int32_t v = ok ? (int32_t)rings[q + (unsigned)k] : WNULL;
+          const unsigned hits = __ballot_sync(FULL, ok && k2_in_matrix(v, k, plen, tlen));
+          const unsigned mine = (hits >> (3 * t)) & 7u;  // t <= 10: shift <= 30
+          int found = side ? -1 : 1;                      // empty encoding: lo = 1, hi = -1
+          if (mine) found = side ? chi - (__ffs((int)mine) - 1) : clo + __ffs((int)mine) - 1;
+          unsigned unres = __ballot_sync(FULL, j == 0 && en && !mine && chi - clo + 1 > 3);
+          if (j == 0 && t < 2 * ncomp) meta[2 * D[K2_D_OSLOT + c] + side] = found;
+          while (unres) {  // rare: warp-wide continuation of one scan
+            const int src = __ffs((int)unres) - 1;
+            unres &= unres - 1;
+            const int c2 = __shfl_sync(FULL, c, src), side2 = __shfl_sync(FULL, side, src);
+            const int lo2 = __shfl_sync(FULL, clo, src), hi2 = __shfl_sync(FULL, chi, src);
+            const unsigned q2 = __shfl_sync(FULL, q, src);
+            int f2 = side2 ? -1 : 1;
+            if (!side2) {
+              for (int base = lo2 + 3; base <= hi2; base += 32) {
+                const int kk = base + lane;
+                const unsigned b = __ballot_sync(FULL, (kk <= hi2) && k2_in_matrix(rings[q2 + (unsigned)kk], kk, plen, tlen));
+                if (b) { f2 = base + __ffs((int)b) - 1; break; }
+              }
             } else {
-              const unsigned q = (c == K2_C_M ? wM : c == K2_C_I1 ? wI1 : c == K2_C_D1 ? wD1 : c == K2_C_I2 ? wI2 : wD2) + (unsigned)kbase;
-              bool got = false;
-              if (!side) {
-                for (int base = lo; base <= hi && !got; base += 32) {
-                  const int k = base + lane;
-                  const bool inm = (k <= hi) && k2_in_matrix(rings[q + (unsigned)k], k, plen, tlen);
-                  const unsigned b = __ballot_sync(FULL, inm);
-                  if (b) { found = base + __ffs((int)b) - 1; got = true; }
-                }
-              } else {
-                for (int base = hi; base >= lo && !got; base -= 32) {
-                  const int k = base - lane;
-                  const bool inm = (k >= lo) && k2_in_matrix(rings[q + (unsigned)k], k, plen, tlen);
-                  const unsigned b = __ballot_sync(FULL, inm);
-                  if (b) { found = base - (__ffs((int)b) - 1); got = true; }
-                }
+              for (int base = hi2 - 3; base >= lo2; base -= 32) {
+                const int kk = base - lane;
+                const unsigned b = __ballot_sync(FULL, (kk >= lo2) && k2_in_matrix(rings[q2 + (unsigned)kk], kk, plen, tlen));
+                if (b) { f2 = base - (__ffs((int)b) - 1); break; }
               }
             }
-          }
-          if (lane == 0) {
-            if (C > 1) { for (int r = 0; r < C; ++r) cluster.map_shared_rank(meta, r)[2 * sl + side] = found; }
-            else meta[2 * sl + side] = found;
+            if (lane == 0) meta[2 * D[K2_D_OSLOT + c2] + side2] = f2;
           }
         }
-        if (crank == 0 && tid == 0) { rowoff[s] = bt_used; rowlo[s] = (((lo + kbase) >> 2) << 2) - kbase; cells_acc += (unsigned long long)width; }
+        if (lane == 0) {
+          if (crank == 0) { rowoff[s] = bt_used; rowlo[s] = (g_lo << 2) - kbase; }
+          D64[1] += (unsigned long long)(hi - lo + 1);
+          if (s > 0) D64[0] = bt_used + 4ull * (unsigned long long)(g_hi - g_lo + 1);
+        }
+        __syncwarp();
+        K2_TICK(t_trim);
+        plan(s + 1);
+        K2_TICK(t_plan);
       }
-      if (s > 0) bt_used += bt_row_bytes;
-      csync();  // barrier 2: metadata of score s visible
-      K2_TICK(t_sync);
     }
 
     K2_TICK(t_sync);
+    if (crank == 0 && tid == 0) cells_acc += D64[1];
     // ---- backtrace (warp 0): choice walk to score 0, then forward replay ----
     if (done) {
       csync();  // rowoff/rowlo/bt/oM of the last step visible to warp 0 of rank 0
       if (crank == 0 && warp == 0) {
-        const T* oM = rings + (size_t)slot_of(K2_C_M, s, s) * Wp + kbase;
+        const T* oM = rings + (unsigned)D[K2_D_Q + 7] + kbase;
         const int end_off = oM[end_k];
         int k0 = 0, nb = 0, bad = 0;
         if (lane == 0) {
@@ -937,6 +977,7 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
     K2_TICK(t_bt);
     atomicAdd(P.prof + 0, (unsigned long long)t_cells); atomicAdd(P.prof + 1, (unsigned long long)t_sync);
     atomicAdd(P.prof + 2, (unsigned long long)t_bt); atomicAdd(P.prof + 3, (unsigned long long)t_setup);
+    atomicAdd(P.prof + 4, (unsigned long long)t_trim); atomicAdd(P.prof + 5, (unsigned long long)t_plan);
   }
 #undef K2_TICK
 }

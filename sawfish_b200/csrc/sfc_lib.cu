@@ -517,10 +517,10 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
         max_win = std::max(max_win, (size_t)(d.plen >> 3) + (d.tlen >> 3) + 2);
         max_W = std::max(max_W, Wp);
       }
-      const size_t base = std::min(max_win * 8 + (size_t)nslots * 8 + 64, c->smem_optin);
-      pl->win_cap = (int)((base - (size_t)nslots * 8 - 64) / 8);
+      const size_t base = std::min(max_win * 8 + (size_t)nslots * 8 + K2_MISC_BYTES, c->smem_optin);
+      pl->win_cap = (int)((base - (size_t)nslots * 8 - K2_MISC_BYTES) / 8);
       // cp.async stages for the interior chunks (int32 rings): two per warp when shared memory allows, else one, else none
-      const size_t fixed_sm = ((size_t)pl->win_cap * 8 + (size_t)nslots * 8 + 64 + 15) & ~(size_t)15;
+      const size_t fixed_sm = ((size_t)pl->win_cap * 8 + (size_t)nslots * 8 + K2_MISC_BYTES + 15) & ~(size_t)15;
       const size_t per_stage = (size_t)(threads / 32) * (a.metric == 1 ? K2_SR_N : 2) * K2_SE * 4;
       int stages = wide ? 2 : 0;
       if (const char* e = getenv("SFC_K2_STAGES")) stages = wide ? std::max(0, std::min(3, atoi(e))) : 0;  // experiment knob
@@ -709,9 +709,9 @@ extern "C" int sfc_batch_download(sfc_ctx* c, int32_t* scores, int32_t* status, 
   memcpy(&pool_used, h_misc + 4, 8);
   c->stats.cells = cells;
   if (getenv("SFC_K2_PROF")) {
-    unsigned long long pr[4];
-    memcpy(pr, h_misc + 40, 32);
-    fprintf(stderr, "[k2 prof] cycles of thread 0 summed over CTAs: cells %.3e  barriers+trim %.3e  backtrace+fetch %.3e  setup %.3e\n", (double)pr[0], (double)pr[1], (double)pr[2], (double)pr[3]);
+    unsigned long long pr[6];
+    memcpy(pr, h_misc + 40, 48);
+    fprintf(stderr, "[k2 prof] cycles of thread 0 summed over CTAs: cells %.3e  barrier waits %.3e  backtrace+fetch %.3e  setup %.3e  trim %.3e  plan %.3e\n", (double)pr[0], (double)pr[1], (double)pr[2], (double)pr[3], (double)pr[4], (double)pr[5]);
   }
   if (h_misc[32]) return fail(c, SFC_ERR_UNSUPPORTED, "sequence symbol outside {A,C,G,T,N,a,c,g,t,n}");
   int ret = SFC_OK;
