@@ -157,7 +157,7 @@ __device__ __forceinline__ void k2_prefetch_l2(const void* p) { asm volatile("pr
 // 16-byte units [e0w-4, e0w+132) of every row are copied global -> shared with cp.async (LDGSTS, L2 -> smem, no
 // registers held across the latency) one or two chunks ahead of the compute, so the ~1 us ring-load latency that
 // used to stall every chunk (45% of all warp samples: long scoreboard) overlaps the previous chunk's arithmetic.
-constexpr int K2_SE = 136;                                     // staged elements per row: 4 + 128 + 4
+constexpr int K2_SE = 136;                                     // staged elements per row: 4 + 128 + 4 (544 bytes, see k2_stage_issue)
 enum { K2_SR_MX = 0, K2_SR_MO1, K2_SR_I1E, K2_SR_D1E, K2_SR_I2E, K2_SR_D2E, K2_SR_MO2, K2_SR_N };
 __device__ __forceinline__ void k2_cp16(const int32_t* smem_dst, const int32_t* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -168,31 +168,53 @@ template <int N> __device__ __forceinline__ void k2_cp_wait() { asm volatile("cp
 __device__ __forceinline__ void k2_cp_wait_n(int n) {  // wait until at most n of this thread's groups are pending
   if (n <= 0) k2_cp_wait<0>(); else if (n == 1) k2_cp_wait<1>(); else k2_cp_wait<2>();
 }
-// lane L copies its own group (unit L+1) of every needed row; lanes 0 / 31 also copy the unit left / right of the chunk
+// lane L copies its own group (unit L+1) of every needed row; lanes 0 / 31 also copy the unit left / right of the chunk.
+// All copies of a chunk are issued from ONE asm block each (own rows / edge units) so that every source address
+// sits in its own register pair: ptxas otherwise recycles one pair, and each LDGSTS then waits (long scoreboard) for
+// its predecessor to release it.
 template <bool AFF>
 __device__ __forceinline__ void k2_stage_issue(int32_t* stg, const K2Rows<int32_t>& q, unsigned e0w, bool has2, bool mo2, int lane) {
   const unsigned eo = e0w + ((unsigned)lane << 2);
-  int32_t* d = stg + 4 + (lane << 2);
-  const bool lx = lane == 0 && e0w >= 4u;  // the leftmost boundary chunk can start at element 0 of the row
-  const bool ex = lx || (lane == 31);
-  const int xo = lane == 0 ? -4 : 4;
-  k2_cp16(d + K2_SR_MX * K2_SE, q.R + (q.pMX + eo));
-  k2_cp16(d + K2_SR_MO1 * K2_SE, q.R + (q.pMO1 + eo));
-  if (ex) k2_cp16(d + K2_SR_MO1 * K2_SE + xo, q.R + (q.pMO1 + eo + (unsigned)xo));
+  const unsigned d = (unsigned)__cvta_generic_to_shared(stg + 4 + (lane << 2));
+  const int32_t* R = q.R;
   if (AFF) {
-    k2_cp16(d + K2_SR_I1E * K2_SE, q.R + (q.pI1E + eo));
-    k2_cp16(d + K2_SR_D1E * K2_SE, q.R + (q.pD1E + eo));
-    if (lx) k2_cp16(d + K2_SR_I1E * K2_SE - 4, q.R + (q.pI1E + eo - 4u));
-    if (lane == 31) k2_cp16(d + K2_SR_D1E * K2_SE + 4, q.R + (q.pD1E + eo + 4u));
-    if (has2) {
-      k2_cp16(d + K2_SR_I2E * K2_SE, q.R + (q.pI2E + eo));
-      k2_cp16(d + K2_SR_D2E * K2_SE, q.R + (q.pD2E + eo));
-      if (lx) k2_cp16(d + K2_SR_I2E * K2_SE - 4, q.R + (q.pI2E + eo - 4u));
-      if (lane == 31) k2_cp16(d + K2_SR_D2E * K2_SE + 4, q.R + (q.pD2E + eo + 4u));
-      if (mo2) {
-        k2_cp16(d + K2_SR_MO2 * K2_SE, q.R + (q.pMO2 + eo));
-        if (ex) k2_cp16(d + K2_SR_MO2 * K2_SE + xo, q.R + (q.pMO2 + eo + (unsigned)xo));
-      }
+    asm volatile(
+        "{\n .reg .pred p2, pm;\n setp.ne.b32 p2, %8, 0;\n setp.ne.b32 pm, %9, 0;\n"
+        " cp.async.cg.shared.global [%0], [%1], 16;\n"
+        " cp.async.cg.shared.global [%0+544], [%2], 16;\n"
+        " cp.async.cg.shared.global [%0+1088], [%3], 16;\n"
+        " cp.async.cg.shared.global [%0+1632], [%4], 16;\n"
+        " @p2 cp.async.cg.shared.global [%0+2176], [%5], 16;\n"
+        " @p2 cp.async.cg.shared.global [%0+2720], [%6], 16;\n"
+        " @pm cp.async.cg.shared.global [%0+3264], [%7], 16;\n}"
+        ::"r"(d), "l"(R + (q.pMX + eo)), "l"(R + (q.pMO1 + eo)), "l"(R + (q.pI1E + eo)), "l"(R + (q.pD1E + eo)),
+          "l"(R + (q.pI2E + eo)), "l"(R + (q.pD2E + eo)), "l"(R + (q.pMO2 + eo)), "r"((int)has2), "r"((int)(has2 && mo2))
+        : "memory");
+    const bool left = lane == 0;
+    if ((left && e0w >= 4u) || lane == 31) {  // the leftmost boundary chunk can start at element 0 of a row
+      const unsigned xo = left ? (unsigned)-4 : 4u;
+      const unsigned r1 = left ? K2_SR_I1E : K2_SR_D1E, r2 = left ? K2_SR_I2E : K2_SR_D2E;
+      const unsigned p1 = left ? q.pI1E : q.pD1E, p2 = left ? q.pI2E : q.pD2E;
+      const unsigned dx = d + xo * 4u;
+      asm volatile(
+          "{\n .reg .pred p2, pm;\n setp.ne.b32 p2, %8, 0;\n setp.ne.b32 pm, %9, 0;\n"
+          " cp.async.cg.shared.global [%0], [%1], 16;\n"
+          " cp.async.cg.shared.global [%2], [%3], 16;\n"
+          " @p2 cp.async.cg.shared.global [%4], [%5], 16;\n"
+          " @pm cp.async.cg.shared.global [%6], [%7], 16;\n}"
+          ::"r"(dx + K2_SR_MO1 * K2_SE * 4u), "l"(R + (q.pMO1 + eo + xo)), "r"(dx + r1 * K2_SE * 4u), "l"(R + (p1 + eo + xo)),
+            "r"(dx + r2 * K2_SE * 4u), "l"(R + (p2 + eo + xo)), "r"(dx + K2_SR_MO2 * K2_SE * 4u), "l"(R + (q.pMO2 + eo + xo)),
+            "r"((int)has2), "r"((int)(has2 && mo2))
+          : "memory");
+    }
+  } else {
+    asm volatile(
+        "{\n cp.async.cg.shared.global [%0], [%1], 16;\n cp.async.cg.shared.global [%0+544], [%2], 16;\n}"
+        ::"r"(d), "l"(R + (q.pMX + eo)), "l"(R + (q.pMO1 + eo)) : "memory");
+    const bool left = lane == 0;
+    if ((left && e0w >= 4u) || lane == 31) {
+      const unsigned xo = left ? (unsigned)-4 : 4u;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + xo * 4u + K2_SR_MO1 * K2_SE * 4u), "l"(R + (q.pMO1 + eo + xo)) : "memory");
     }
   }
 }
