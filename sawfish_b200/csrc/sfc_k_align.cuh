@@ -843,18 +843,24 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
             const int lo2 = __shfl_sync(FULL, clo, src), hi2 = __shfl_sync(FULL, chi, src);
             const unsigned q2 = __shfl_sync(FULL, q, src);
             int f2 = side2 ? -1 : 1;
-            if (!side2) {
-              for (int base = lo2 + 3; base <= hi2; base += 32) {
-                const int kk = base + lane;
-                const unsigned b = __ballot_sync(FULL, (kk <= hi2) && k2_in_matrix(rings[q2 + (unsigned)kk], kk, plen, tlen));
-                if (b) { f2 = base + __ffs((int)b) - 1; break; }
+            // 256 diagonals per round (eight loads in flight): the ranges behind a sequence end, where every gap entry
+            // is out of matrix, can be hundreds of diagonals wide and are rescanned at every score
+            for (int base = side2 ? hi2 - 3 : lo2 + 3; side2 ? base >= lo2 : base <= hi2; base += side2 ? -256 : 256) {
+              ++t_setup;
+              int32_t pv8[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int kk = side2 ? base - 32 * u - lane : base + 32 * u + lane;
+                pv8[u] = (kk >= lo2 && kk <= hi2) ? (int32_t)rings[q2 + (unsigned)kk] : WNULL;
               }
-            } else {
-              for (int base = hi2 - 3; base >= lo2; base -= 32) {
-                const int kk = base - lane;
-                const unsigned b = __ballot_sync(FULL, (kk >= lo2) && k2_in_matrix(rings[q2 + (unsigned)kk], kk, plen, tlen));
-                if (b) { f2 = base - (__ffs((int)b) - 1); break; }
+              bool got = false;
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int kk = side2 ? base - 32 * u - lane : base + 32 * u + lane;
+                const unsigned b = __ballot_sync(FULL, kk >= lo2 && kk <= hi2 && k2_in_matrix(pv8[u], kk, plen, tlen));
+                if (b && !got) { got = true; f2 = side2 ? base - 32 * u - (__ffs((int)b) - 1) : base + 32 * u + __ffs((int)b) - 1; }
               }
+              if (got) break;
             }
             if (lane == 0) meta[2 * D[K2_D_OSLOT + c2] + side2] = f2;
           }
@@ -1000,6 +1006,8 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
     atomicAdd(P.prof + 0, (unsigned long long)t_cells); atomicAdd(P.prof + 1, (unsigned long long)t_sync);
     atomicAdd(P.prof + 2, (unsigned long long)t_bt); atomicAdd(P.prof + 3, (unsigned long long)t_setup);
     atomicAdd(P.prof + 4, (unsigned long long)t_trim); atomicAdd(P.prof + 5, (unsigned long long)t_plan);
+    atomicMax(P.prof + 6, (unsigned long long)(t_cells + t_sync + t_bt + t_setup + t_trim + t_plan));  // busiest CTA
+    atomicAdd(P.prof + 7, 1ull);
   }
 #undef K2_TICK
 }

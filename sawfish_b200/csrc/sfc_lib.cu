@@ -709,9 +709,9 @@ extern "C" int sfc_batch_download(sfc_ctx* c, int32_t* scores, int32_t* status, 
   memcpy(&pool_used, h_misc + 4, 8);
   c->stats.cells = cells;
   if (getenv("SFC_K2_PROF")) {
-    unsigned long long pr[6];
-    memcpy(pr, h_misc + 40, 48);
-    fprintf(stderr, "[k2 prof] cycles of thread 0 summed over CTAs: cells %.3e  barrier waits %.3e  backtrace+fetch %.3e  setup %.3e  trim %.3e  plan %.3e\n", (double)pr[0], (double)pr[1], (double)pr[2], (double)pr[3], (double)pr[4], (double)pr[5]);
+    unsigned long long pr[8];
+    memcpy(pr, h_misc + 40, 64);
+    fprintf(stderr, "[k2 prof] cycles of thread 0 summed over %llu CTAs: cells %.3e  barrier waits %.3e  backtrace+fetch %.3e  setup %.3e  trim %.3e  plan %.3e | busiest CTA %.3e\n", pr[7], (double)pr[0], (double)pr[1], (double)pr[2], (double)pr[3], (double)pr[4], (double)pr[5], (double)pr[6]);
   }
   if (h_misc[32]) return fail(c, SFC_ERR_UNSUPPORTED, "sequence symbol outside {A,C,G,T,N,a,c,g,t,n}");
   int ret = SFC_OK;
@@ -931,8 +931,11 @@ extern "C" int sfc_aligner_align(sfc_aligner* a, const uint8_t* pattern, size_t 
 // ============================================================================ sharding helpers
 namespace {
 double estimate_work(const AdjPen& a, double plen, double tlen, double pbf, double tbf) {
-  const double dl = std::abs(plen - tlen);
+  double dl = std::abs(plen - tlen);
+  static const int mode = getenv("SFC_EST") ? atoi(getenv("SFC_EST")) : 0;
+  if (mode == 1) dl = std::max(0.0, tlen > plen ? (tlen - plen) - 2.0 * tbf : (plen - tlen) - 2.0 * pbf);
   const double es = (double)gap_cost(a, (long long)dl) + 0.012 * 0.5 * (plen + tlen) + 8.0;  // expected final score
+  if (mode == 1) return es * std::min(pbf + tbf + 1.0 + es, plen + tlen + 1.0);
   return es * (pbf + tbf + 1.0 + 0.4 * es);                                                   // x mean wavefront width
 }
 }  // namespace
