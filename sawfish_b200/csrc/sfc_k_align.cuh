@@ -36,6 +36,8 @@ enum { K2_C_M = 0, K2_C_I1 = 1, K2_C_D1 = 2, K2_C_I2 = 3, K2_C_D2 = 4 };
 enum { K2_D_S = 0, K2_D_STATUS, K2_D_LO, K2_D_HI, K2_D_HAS2, K2_D_G1A, K2_D_G1B, K2_D_G2A, K2_D_G2B, K2_D_M2A, K2_D_M2B,
        K2_D_Q = 12 /* 12 row offsets */, K2_D_RLO = 24 /* 7 */, K2_D_RCNT = 31 /* 7 */, K2_D_OSLOT = 38 /* 5 */,
        K2_D_CLO = 43 /* 5: raw (untrimmed) range of each output component, */, K2_D_CHI = 48 /* 5 */,
+       K2_D_WIDE = 220 /* 10: width of the out-of-matrix run each trim scan crossed at the previous score */,
+       K2_D_CAND = 230 /* 10: first hit of the cooperative wide scans */, K2_D_ANYW = 240 /* any K2_D_WIDE > 3 */,
        K2_D_BT = 58 /* index from misc: two 64-bit counters */, K2_D_TAB = 64 /* index from misc: plan table [32 lanes][5] */ };
 constexpr int K2_MISC_BYTES = 1024;  // misc area behind the range metadata: pair index, terminating diagonal, plan
 
@@ -528,7 +530,8 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
       __syncwarp();
     };
     if (warp == 0) {
-      if (lane == 0) { D[K2_D_STATUS] = 0; D64[0] = 0; D64[1] = 0; }
+      if (lane == 0) { D[K2_D_STATUS] = 0; D64[0] = 0; D64[1] = 0; D[K2_D_ANYW] = 0; }
+      if (lane < 10) { D[K2_D_WIDE + lane] = 0; D[K2_D_CAND + lane] = (lane & 1) ? INT_MIN : INT_MAX; }
       {  // plan table: rows 0..6 sources in staging order (MX, MO1, I1E, D1E, I2E, D2E, MO2); rows 7..11 outputs (M, I1, D1, I2, D2)
         int comp = K2_C_M, back = 0, dl = 0, dh = 0, il = 0, ih = 0;
         switch (lane) {
@@ -818,6 +821,41 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
       }
       // ---- warp 0 (of every CTA of a cluster, redundantly): trim the rows of score s, then plan the next score ----
       K2_TICK(t_sync);
+      // Behind a sequence end (pattern or text exhausted, common when the text window is much longer than the contig)
+      // every gap entry is out of matrix on hundreds to thousands of diagonals, and each score's trim has to cross
+      // that run again.  A scan that crossed a long run at the previous score is therefore done by ALL warps together
+      // (a slice each, one load latency), sized by that run, before warp 0 finishes the trims.
+      if (D[K2_D_ANYW]) {
+        for (int t = 0; t < 2 * ncomp; ++t) {
+          const int w = D[K2_D_WIDE + t];
+          if (w <= 3) continue;
+          const int c = t >> 1, side = t & 1;
+          if (!((c == K2_C_M || s > 0) && !((c == K2_C_I2 || c == K2_C_D2) && !has2))) continue;
+          const int clo = D[K2_D_CLO + c], chi = D[K2_D_CHI + c];
+          const unsigned q = (unsigned)D[K2_D_Q + 7 + c] + (unsigned)kbase;
+          const int win = min(w + 64, chi - clo + 1);
+          const int per = min((win + NW * 32 - 1) / (NW * 32), 8);  // 32-diagonal blocks per warp
+          const int o = warp * per * 32;                              // my slice, in scan order from the edge
+          int32_t pv8[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int off = o + 32 * u + lane;
+            const int kk = side ? chi - off : clo + off;
+            pv8[u] = (u < per && off < win) ? (int32_t)rings[q + (unsigned)kk] : WNULL;
+          }
+          bool got = false;
+          int pos = 0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int off = o + 32 * u + lane;
+            const int kk = side ? chi - off : clo + off;
+            const unsigned b = __ballot_sync(FULL, u < per && off < win && k2_in_matrix(pv8[u], kk, plen, tlen));
+            if (b && !got) { got = true; const int fo = o + 32 * u + __ffs((int)b) - 1; pos = side ? chi - fo : clo + fo; }
+          }
+          if (got && lane == 0) { if (side) atomicMax(D + K2_D_CAND + t, pos); else atomicMin(D + K2_D_CAND + t, pos); }
+        }
+        __syncthreads();
+      }
       if (warp == 0) {
         // trim every component of score s to its first / last in-matrix diagonal (metadata only).  All ten scans
         // (5 components x 2 sides) probe their first three diagonals with ONE load: lane 3t+j reads diagonal j of scan t,
@@ -828,24 +866,41 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
           const int clo = en ? D[K2_D_CLO + c] : 1, chi = en ? D[K2_D_CHI + c] : -1;
           const unsigned q = (unsigned)D[K2_D_Q + 7 + c] + (unsigned)kbase;
           const int k = side ? chi - j : clo + j;
-          const bool ok = k >= clo && k <= chi;
+          const int wprev = (t < 10 && D[K2_D_ANYW]) ? D[K2_D_WIDE + t] : 0;
+          const bool wide = en && wprev > 3;  // scanned by all warps above: first hit (if any) in K2_D_CAND
+          const bool ok = !wide && k >= clo && k <= chi;
           const int32_t v = ok ? (int32_t)rings[q + (unsigned)k] : WNULL;
           const unsigned hits = __ballot_sync(FULL, ok && k2_in_matrix(v, k, plen, tlen));
           const unsigned mine = (hits >> (3 * t)) & 7u;  // t <= 10: shift <= 30
           int found = side ? -1 : 1;                      // empty encoding: lo = 1, hi = -1
+          bool got = mine != 0u;
+          int skip = 3;                                   // diagonals already examined from the edge
           if (mine) found = side ? chi - (__ffs((int)mine) - 1) : clo + __ffs((int)mine) - 1;
-          unsigned unres = __ballot_sync(FULL, j == 0 && en && !mine && chi - clo + 1 > 3);
-          if (j == 0 && t < 2 * ncomp) meta[2 * D[K2_D_OSLOT + c] + side] = found;
+          if (wide) {
+            const int cand = D[K2_D_CAND + t];
+            got = side ? cand != INT_MIN : cand != INT_MAX;
+            if (got) found = cand;
+            const int win = min(wprev + 64, chi - clo + 1);
+            skip = min(win, min((win + NW * 32 - 1) / (NW * 32), 8) * NW * 32);
+          }
+          unsigned unres = __ballot_sync(FULL, j == 0 && en && !got && chi - clo + 1 > skip);
+          if (j == 0 && t < 2 * ncomp) {
+            meta[2 * D[K2_D_OSLOT + c] + side] = found;
+            // remember how long an out-of-matrix run this scan crossed: the next score's scan is sized by it
+            D[K2_D_WIDE + t] = !en ? 0 : got ? (side ? chi - found : found - clo) : chi - clo + 1;
+            D[K2_D_CAND + t] = side ? INT_MIN : INT_MAX;
+          }
           while (unres) {  // rare: warp-wide continuation of one scan
             const int src = __ffs((int)unres) - 1;
             unres &= unres - 1;
             const int c2 = __shfl_sync(FULL, c, src), side2 = __shfl_sync(FULL, side, src);
             const int lo2 = __shfl_sync(FULL, clo, src), hi2 = __shfl_sync(FULL, chi, src);
             const unsigned q2 = __shfl_sync(FULL, q, src);
+            const int skip2 = __shfl_sync(FULL, skip, src), t2 = __shfl_sync(FULL, t, src);
             int f2 = side2 ? -1 : 1;
             // 256 diagonals per round (eight loads in flight): the ranges behind a sequence end, where every gap entry
             // is out of matrix, can be hundreds of diagonals wide and are rescanned at every score
-            for (int base = side2 ? hi2 - 3 : lo2 + 3; side2 ? base >= lo2 : base <= hi2; base += side2 ? -256 : 256) {
+            for (int base = side2 ? hi2 - skip2 : lo2 + skip2; side2 ? base >= lo2 : base <= hi2; base += side2 ? -256 : 256) {
               ++t_setup;
               int32_t pv8[8];
 #pragma unroll
@@ -862,8 +917,15 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
               }
               if (got) break;
             }
-            if (lane == 0) meta[2 * D[K2_D_OSLOT + c2] + side2] = f2;
+            if (lane == 0) {
+              meta[2 * D[K2_D_OSLOT + c2] + side2] = f2;
+              if (side2 ? f2 >= lo2 : f2 <= hi2) D[K2_D_WIDE + t2] = side2 ? hi2 - f2 : f2 - lo2;  // found (else the whole range was recorded)
+            }
           }
+          __syncwarp();
+          const bool anyw = lane < 2 * ncomp && D[K2_D_WIDE + min(lane, 9)] > 3;
+          const unsigned aw = __ballot_sync(FULL, anyw);
+          if (lane == 0) D[K2_D_ANYW] = aw != 0u;
         }
         if (lane == 0) {
           if (crank == 0) { rowoff[s] = bt_used; rowlo[s] = (g_lo << 2) - kbase; }
