@@ -638,6 +638,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     // ---- escalation passes for pairs that ran out of slab (-6) or of pool (-4) ----
     std::vector<uint32_t> retry, cur(c->h_order.begin() + k2s_begin, c->h_order.end());
     int divisor = 1;
+    const int force_c_env = getenv("SFC_K2_CLUSTER") ? atoi(getenv("SFC_K2_CLUSTER")) : 0;
     for (int pass = 0; pass < 12; ++pass) {
       c->h_status.resize(n);
       CU(cudaMemcpyAsync(c->h_status.data(), c->d_status.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -666,12 +667,17 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       }
       divisor *= 4;
       Plan pl;
-      if ((rc = plan_job(retry, K2_LB_T, 1, avail, divisor, &pl))) return rc;
+      // the pairs that ran out of choice bytes are the heaviest ones: when few are left, spread each over a cluster
+      int Cr = 1;
+      for (int cc = 8; cc > 1; cc >>= 1)
+        if (retry.size() * (size_t)cc <= (size_t)c->sm_count * 7 / 8) { Cr = cc; break; }
+      if (force_c_env > 0) Cr = force_c_env;
+      if ((rc = plan_job(retry, K2_LB_T, Cr, avail, divisor, &pl))) return rc;
       if ((rc = ensure(c, c->d_ws, pl.slab * pl.n_cl))) return rc;
       cur = retry;
       CU(cudaMemcpyAsync((uint32_t*)c->d_order.p + k2s_begin, retry.data(), retry.size() * 4, cudaMemcpyHostToDevice, c->stream));
       CU(cudaMemsetAsync(misc + 8, 0, 4, c->stream));
-      if ((rc = launch_job((const uint32_t*)c->d_order.p + k2s_begin, retry.size(), K2_LB_T, 1, pl, (unsigned char*)c->d_ws.p, misc + 8, c->stream))) return rc;
+      if ((rc = launch_job((const uint32_t*)c->d_order.p + k2s_begin, retry.size(), K2_LB_T, Cr, pl, (unsigned char*)c->d_ws.p, misc + 8, c->stream))) return rc;
       if (pl.n_cl == 1 && pl.slab >= avail - 4096 && !pool_short) divisor = 1 << 20;  // last resort was tried
     }
   }
