@@ -9,10 +9,13 @@
 //   * sequences: 4-bit, overlapped 8-byte windows in shared memory (one LDS.64 + one funnel shift per
 //     8-base compare; warp-cooperative 256-base rounds for long match runs);
 //   * wavefront rings (M depth max(x',o1'+e1',o2'+e2')+1, I1/D1 depth e1'+1, I2/D2 depth e2'+1) live in
-//     the CTA's slab of device memory (HBM/L2) — a 20 kb x 20 kb pair needs ~22 MB of ring;
+//     the CTA's slab of device memory (HBM/L2) — a 20 kb x 20 kb pair needs ~22 MB of ring; a warp's chunk of
+//     every source row is staged global -> shared with cp.async one chunk ahead of the arithmetic;
 //   * reads of source wavefronts are range-guarded from per-wavefront (lo,hi) metadata kept in shared
 //     memory, so rings are never initialised or cleared; trimming of every component to its first/last
-//     in-matrix diagonal is metadata only (ten tiny warp scans from the row ends per score);
+//     in-matrix diagonal is metadata only (warp 0 probes the row ends between the two barriers of a score);
+//   * everything a score step needs besides the cells (ring slots, ranges, chunk classification) is planned once
+//     per CTA by warp 0, one lane per ring row, and published in shared memory;
 //   * backtrace: instead of keeping every wavefront (WFA2 MemoryHigh) the kernel records ONE choice byte per
 //     (score, diagonal) at compute time using WFA2's tie-break priority
 //     (X > D2 > D1 > I2 > I1, extend >= open), walks the bytes back to score 0 (also yields k0 for the
