@@ -573,6 +573,7 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
       s = D[K2_D_S];
       const int lo = D[K2_D_LO], hi = D[K2_D_HI];
       const bool has2 = D[K2_D_HAS2] != 0;
+      const bool anyw_s = D[K2_D_ANYW] != 0;  // read here: warp 0 rewrites it while other warps may still be behind barrier 1
       const int G1A = D[K2_D_G1A], G1B = D[K2_D_G1B], G2A = D[K2_D_G2A], G2B = D[K2_D_G2B], M2A = D[K2_D_M2A], M2B = D[K2_D_M2B];
       const unsigned long long bt_used = D64[0];
       const T* __restrict__ R = rings;
@@ -828,7 +829,7 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
       // every gap entry is out of matrix on hundreds to thousands of diagonals, and each score's trim has to cross
       // that run again.  A scan that crossed a long run at the previous score is therefore done by ALL warps together
       // (a slice each, one load latency), sized by that run, before warp 0 finishes the trims.
-      if (D[K2_D_ANYW]) {
+      if (anyw_s) {
         for (int t = 0; t < 2 * ncomp; ++t) {
           const int w = D[K2_D_WIDE + t];
           if (w <= 3) continue;
@@ -869,7 +870,7 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
           const int clo = en ? D[K2_D_CLO + c] : 1, chi = en ? D[K2_D_CHI + c] : -1;
           const unsigned q = (unsigned)D[K2_D_Q + 7 + c] + (unsigned)kbase;
           const int k = side ? chi - j : clo + j;
-          const int wprev = (t < 10 && D[K2_D_ANYW]) ? D[K2_D_WIDE + t] : 0;
+          const int wprev = (t < 10 && anyw_s) ? D[K2_D_WIDE + t] : 0;
           const bool wide = en && wprev > 3;  // scanned by all warps above: first hit (if any) in K2_D_CAND
           const bool ok = !wide && k >= clo && k <= chi;
           const int32_t v = ok ? (int32_t)rings[q + (unsigned)k] : WNULL;
