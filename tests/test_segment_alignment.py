@@ -1,0 +1,106 @@
+"""Two-region CIGAR consumer and breakend homology: the reference's own known answers.
+
+Golden vectors: src/refine_sv/align/segment_alignment.rs:366-668 (six tests) and
+lib/rust-vc-utils/src/indel_breakend_homology.rs:79-147 (two tests), restated as data.
+"""
+import numpy as np
+import pytest
+
+from sawfish_b200.indel_breakend_homology import get_indel_breakend_homology_info
+from sawfish_b200.segment_alignment import (TwoRegionAltHapInfo, does_alignment_support_alt_hap,
+                                            transform_alt_hap_alignment_into_left_right_components)
+from sawfish_b200.simple_alignment import SimpleAlignment, cigar_from_string, cigar_to_string
+
+
+def base_info(seq=b"TTTTACTGACTGTTTNNNNTTTACTGACTGTTTT", spacer=(15, 19), left_pin=False, right_pin=False):
+    return TwoRegionAltHapInfo(alt_hap_seq=seq, spacer_range=spacer, left_boundary_pin=left_pin, right_boundary_pin=right_pin)
+
+
+def run(cigar, info, contig, anchor=3, ref_offset=4):
+    return transform_alt_hap_alignment_into_left_right_components(anchor, SimpleAlignment(ref_offset, cigar_from_string(cigar)),
+                                                                  info, contig)
+
+
+def check(res, left_off, left_cigar, right_off, right_cigar, hom_range, hom_seq=None):
+    assert res is not None
+    assert res.left_alignment.ref_offset == left_off and cigar_to_string(res.left_alignment.cigar) == left_cigar
+    assert res.right_alignment.ref_offset == right_off and cigar_to_string(res.right_alignment.cigar) == right_cigar
+    assert res.left_right_breakend_homology_range == hom_range
+    if hom_seq is not None:
+        assert res.left_right_breakend_homology_seq == hom_seq
+
+
+def test_plain_split_and_anchor_requirement():  # segment_alignment.rs:389-430
+    contig = b"ACTGACTGACTGACTG"
+    assert run("8=10D8=", base_info(), contig, anchor=10) is None
+    check(run("8=10D8=", base_info(), contig), 4, "8=8S", 3, "8S8=", (0, 0))
+
+
+def test_breakend_homology():  # :432-470
+    info = base_info(seq=b"TTTTACTGACTGACCNNNNTTTACTGACTGTTTT")
+    check(run("8=10D8=", info, b"ACTGACTGACTGACTG"), 4, "8=8S", 3, "8S8=", (0, 2), b"AC")
+
+
+def test_insertion_right_of_the_breakend():  # :472-504
+    check(run("8=10D4I8=", base_info(), b"ACTGACTGCCCCACTGACTG"), 4, "8=12S", 3, "12S8=", (0, 0))
+
+
+def test_insertion_left_of_the_breakend():  # :506-538
+    check(run("8=4I10D8=", base_info(), b"ACTGACTGCCCCACTGACTG"), 4, "8=12S", 3, "12S8=", (0, 0))
+
+
+def test_left_pin():  # :540-602
+    seq = b"TTTTACTGACTGNNNNTTTACTGACTGTTTT"
+    contig = b"ACTGACTGACTGACTG"
+    check(run("8=7D8=", base_info(seq, (12, 16), left_pin=True), contig), 4, "8=8S", 3, "8S8=", (0, 0))
+    assert run("8=7D8=", base_info(seq, (12, 16), left_pin=False), contig) is None
+
+
+def test_right_pin():  # :604-668
+    seq = b"TTTTACTGACTGTTTNNNNACTGACTGTTTT"
+    check(run("8=7D8=", base_info(seq, (15, 19), right_pin=True), b"ACTGACTGACTGACTG"), 4, "8=8S", 0, "8S8=", (0, 0))
+
+
+def test_rejections():
+    info = base_info()
+    contig = b"ACTGACTGACTGACTG"
+    # a match block across the spacer, and an op that ends inside it (segment_alignment.rs:232-248)
+    assert run("8=3X4=3X8=", info, b"A" * 26) is None
+    assert run("8=5D3D8=", info, contig) is None
+    assert not does_alignment_support_alt_hap(3, SimpleAlignment(4, cigar_from_string("8=10D2=")), 15, 19)
+
+
+def test_indel_homology_range():  # indel_breakend_homology.rs:79-119
+    seq1, seq2 = b"ABCDDABC", b"ABCDDDABC"
+    assert get_indel_breakend_homology_info(seq2, (3, 4), seq1, (3, 3)) == ((0, 2), b"DD")
+    assert get_indel_breakend_homology_info(seq1, (3, 3), seq2, (3, 4)) == ((0, 2), b"DD")
+    assert get_indel_breakend_homology_info(seq2, (5, 6), seq1, (5, 5)) == ((-2, 0), b"DD")
+    assert get_indel_breakend_homology_info(seq1, (5, 5), seq2, (5, 6)) == ((-2, 0), b"DD")
+
+
+def test_indel_homology_range_edges():  # :121-147
+    assert get_indel_breakend_homology_info(b"DDDDDDABC", (3, 4), b"DDDDABC", (2, 2)) == ((-2, 2), b"DDDD")
+    assert get_indel_breakend_homology_info(b"ABCDDDDDD", (3, 4), b"ABCDDDD", (3, 3)) == ((0, 4), b"DDDD")
+
+
+@pytest.mark.gpu
+def test_two_region_pair_through_the_cuda_path():
+    """Breakpoint-shaped pair (segment 1 + 100 x N + segment 2, src/refine_sv/align/mod.rs:712-737) aligned by K2,
+    its CIGAR split by the consumer: the spacer must be crossed by one deletion and both sides anchored."""
+    from sawfish_b200.batch import AlignContext
+    from sawfish_b200.refine_sv_align import align_contigs_batch
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    seg1, seg2 = acgt[rng.integers(0, 4, 4000)].tobytes(), acgt[rng.integers(0, 4, 4200)].tobytes()
+    alt_hap = seg1 + b"N" * 100 + seg2
+    contig = seg1[-1800:] + seg2[:1800]
+    ctx = AlignContext(0)
+    (score, aln), = align_contigs_batch(ctx, [alt_hap], [(0, contig)])
+    assert aln is not None
+    info = TwoRegionAltHapInfo(alt_hap_seq=alt_hap, spacer_range=(4000, 4100))
+    res = transform_alt_hap_alignment_into_left_right_components(50, aln, info, contig)
+    assert res is not None
+    assert res.left_alignment.ref_offset == 4000 - 1800 and cigar_to_string(res.left_alignment.cigar) == "1800=1800S"
+    assert res.right_alignment.ref_offset == 0 and cigar_to_string(res.right_alignment.cigar) == "1800S1800="
+    lo, hi = res.left_right_breakend_homology_range
+    assert lo <= 0 <= hi and len(res.left_right_breakend_homology_seq) == hi - lo
