@@ -95,3 +95,36 @@ def get_single_region_indel_candidates(alignment: SimpleAlignment, chrom_pos: in
     if is_large_insertion:
         return [c for c in refined if c.ins_len > MIN_LARGE_INSERTION_LEN]
     return refined
+
+
+@dataclass
+class NormalizedIndel:
+    """Breakend description of one indel candidate after homology normalisation (the part of the reference's RefinedSV
+    that depends on the alignment): half-open chromosome ranges, left-shifted positions, homology and insert sequence."""
+    breakend1_range: Tuple[int, int]
+    breakend2_range: Tuple[int, int]
+    chrom_pos: int
+    contig_pos: int
+    breakend1_homology_seq: bytes
+    insert_seq: bytes
+    contig_pos_before_breakend1: int
+
+
+def normalize_indel_candidate(chrom_pos: int, del_len: int, ins_len: int, contig_pos: int, contig_seq: bytes,
+                              chrom_segment_start: int, chrom_segment_seq: bytes) -> NormalizedIndel:
+    """Homology range of the indel, left shift, and the two breakend intervals: the alignment-dependent core of
+    create_indel_refined_sv_candidate (src/refine_sv/align/mod.rs:71-150). This is why the placement of a clean indel
+    inside its homology range by the aligner's tie-break is not observable in the candidate VCF."""
+    from .indel_breakend_homology import get_indel_breakend_homology_info
+    assert chrom_segment_start <= chrom_pos
+    seg_pos = chrom_pos - chrom_segment_start
+    (h0, h1), hom_seq = get_indel_breakend_homology_info(chrom_segment_seq, (seg_pos, seg_pos + del_len), contig_seq,
+                                                         (contig_pos, contig_pos + ins_len))
+    chrom_pos += h0  # left shift
+    contig_pos += h0
+    hom_len = h1 - h0
+    b1 = (chrom_pos - 1, chrom_pos + hom_len)
+    b2 = (chrom_pos - 1 + del_len, chrom_pos + del_len + hom_len)
+    assert contig_pos >= 1
+    return NormalizedIndel(b1, b2, chrom_pos, contig_pos, hom_seq, bytes(contig_seq[contig_pos:contig_pos + ins_len]),
+                           contig_pos - 1)

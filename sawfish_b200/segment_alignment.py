@@ -138,3 +138,44 @@ def transform_alt_hap_alignment_into_left_right_components(
                                                           sv_contig_range)
     return AltHapLeftRightComponentAlignmentInfo(SimpleAlignment(alignment.ref_offset, left_cigar),
                                                  SimpleAlignment(right_offset, right_cigar), hom_range, hom_seq)
+
+
+def collapse_indels_at_breakpoint(alt_hap_info: TwoRegionAltHapInfo, alignment: SimpleAlignment,
+                                  min_assembly_collapse_anchor: int = 4) -> None:
+    """Fold every edit between the last >= 4-base `=` anchor before the spacer and the first one after it into a single
+    insertion + deletion at the breakpoint, in place (src/refine_sv/align/mod.rs:1416-1518). Applied to K2's CIGAR
+    before the left/right split so that breakpoint insertions are represented the same way whatever the aligner's
+    tie-breaks did with small edits next to the spacer."""
+    b1, b2 = alt_hap_info.spacer_range
+    anchored1 = anchored2 = False
+    first_edit = last_edit = None
+    pos = alignment.ref_offset
+    for i, (op, n) in enumerate(alignment.cigar):
+        if op == "=":
+            if n >= min_assembly_collapse_anchor:
+                if pos + min_assembly_collapse_anchor < b1:
+                    anchored1, first_edit = True, None  # a later anchor in segment 1 supersedes earlier edits
+                if pos + n - min_assembly_collapse_anchor >= b2:
+                    anchored2 = True
+                    break
+        elif op in "DXI":
+            if anchored1 and first_edit is None:
+                first_edit = i
+            last_edit = i
+        pos += get_cigarseg_ref_offset((op, n))
+    if not (anchored1 and anchored2) or first_edit is None or last_edit is None:
+        return
+    assert last_edit >= first_edit
+    if first_edit == last_edit and alignment.cigar[first_edit][0] == "D":
+        return  # already a clean deletion across the spacer
+    inner = alignment.cigar[first_edit:last_edit + 1]
+    merged: List[Cigar] = []
+    ins = sum(get_cigarseg_read_offset(c, True) for c in inner)
+    dele = sum(get_cigarseg_ref_offset(c) for c in inner)
+    if ins > 0:
+        merged.append(("I", ins))
+    if dele > 0:
+        merged.append(("D", dele))
+    tail = alignment.cigar[last_edit + 1:]
+    # the reference emits the merged pair when it meets the first op after the block, so a block that ends the CIGAR is dropped
+    alignment.cigar = alignment.cigar[:first_edit] + (merged + tail if tail else [])

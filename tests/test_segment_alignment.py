@@ -104,3 +104,26 @@ def test_two_region_pair_through_the_cuda_path():
     assert res.right_alignment.ref_offset == 0 and cigar_to_string(res.right_alignment.cigar) == "1800S1800="
     lo, hi = res.left_right_breakend_homology_range
     assert lo <= 0 <= hi and len(res.left_right_breakend_homology_seq) == hi - lo
+
+
+def test_collapse_indels_at_breakpoint():  # src/refine_sv/align/mod.rs:2271-2341
+    from sawfish_b200.segment_alignment import collapse_indels_at_breakpoint
+    info = TwoRegionAltHapInfo(alt_hap_seq=b"", spacer_range=(300, 400))
+    for cigar_in, expect in [("100=300D100=", "100=300D100="), ("87=10I3=300D100=", "87=13I303D100="),
+                             ("100=300D3=10I87=", "100=13I303D87="), ("96=1X3=300D3=1X96=", "96=8I308D96=")]:
+        aln = SimpleAlignment(100, cigar_from_string(cigar_in))
+        collapse_indels_at_breakpoint(info, aln)
+        assert cigar_to_string(aln.cigar) == expect and aln.ref_offset == 100
+
+
+def test_normalize_indel_candidate_left_shifts_into_homology():
+    from sawfish_b200.refine_sv_align import normalize_indel_candidate
+    # ref ABCDDDABC vs contig ABCDDABC: a 1-base deletion reported at its right-most position (ref 5) moves to ref 3
+    ref, contig = b"ABCDDDABC", b"ABCDDABC"
+    n = normalize_indel_candidate(chrom_pos=1005, del_len=1, ins_len=0, contig_pos=5, contig_seq=contig,
+                                  chrom_segment_start=1000, chrom_segment_seq=ref)
+    assert (n.chrom_pos, n.contig_pos, n.breakend1_homology_seq, n.insert_seq) == (1003, 3, b"DD", b"")
+    assert n.breakend1_range == (1002, 1005) and n.breakend2_range == (1003, 1006) and n.contig_pos_before_breakend1 == 2
+    # the same event reported left-most is a fixed point
+    m = normalize_indel_candidate(1003, 1, 0, 3, contig, 1000, ref)
+    assert (m.chrom_pos, m.breakend1_range, m.breakend2_range) == (1003, (1002, 1005), (1003, 1006))
