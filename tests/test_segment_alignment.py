@@ -93,17 +93,27 @@ def test_two_region_pair_through_the_cuda_path():
     acgt = np.frombuffer(b"ACGT", np.uint8)
     seg1, seg2 = acgt[rng.integers(0, 4, 4000)].tobytes(), acgt[rng.integers(0, 4, 4200)].tobytes()
     alt_hap = seg1 + b"N" * 100 + seg2
-    contig = seg1[-1800:] + seg2[:1800]
     ctx = AlignContext(0)
-    (score, aln), = align_contigs_batch(ctx, [alt_hap], [(0, contig)])
-    assert aln is not None
     info = TwoRegionAltHapInfo(alt_hap_seq=alt_hap, spacer_range=(4000, 4100))
+    # breakends 50 bases inside each segment: the deletion spans the spacer, both sides anchored
+    contig = seg1[2150:3950] + seg2[50:1850]
+    (score, aln), = align_contigs_batch(ctx, [alt_hap], [(0, contig)])
+    assert aln is not None and aln.ref_offset == 2150 and cigar_to_string(aln.cigar) == "1800=200D1800="
     res = transform_alt_hap_alignment_into_left_right_components(50, aln, info, contig)
     assert res is not None
-    assert res.left_alignment.ref_offset == 4000 - 1800 and cigar_to_string(res.left_alignment.cigar) == "1800=1800S"
-    assert res.right_alignment.ref_offset == 0 and cigar_to_string(res.right_alignment.cigar) == "1800S1800="
+    assert res.left_alignment.ref_offset == 2150 and cigar_to_string(res.left_alignment.cigar) == "1800=1800S"
+    assert res.right_alignment.ref_offset == 50 and cigar_to_string(res.right_alignment.cigar) == "1800S1800="
     lo, hi = res.left_right_breakend_homology_range
     assert lo <= 0 <= hi and len(res.left_right_breakend_homology_seq) == hi - lo
+    # contig ending exactly on the last base of segment 1: accepted only when that segment is pinned
+    # (segment_alignment.rs:196-207)
+    contig = seg1[-1800:] + seg2[:1800]
+    (score, aln), = align_contigs_batch(ctx, [alt_hap], [(0, contig)])
+    assert aln is not None and aln.ref_offset == 2200 and cigar_to_string(aln.cigar) == "1800=100D1800="
+    assert transform_alt_hap_alignment_into_left_right_components(50, aln, info, contig) is None
+    info.left_boundary_pin = True
+    res = transform_alt_hap_alignment_into_left_right_components(50, aln, info, contig)
+    assert res is not None and res.right_alignment.ref_offset == 0 and cigar_to_string(res.right_alignment.cigar) == "1800S1800="
 
 
 def test_collapse_indels_at_breakpoint():  # src/refine_sv/align/mod.rs:2271-2341
