@@ -163,6 +163,27 @@ int sfc_multi_last_kernel_ms(const sfc_multi*, double* out);
 /* Runs a dependent-chain-free INT32 micro-benchmark and returns giga-ops/s (thread-level ops). */
 int sfc_measure_int_peak(sfc_ctx*, double* gops_per_s, double* sm_clock_mhz_est);
 
+/* ---- affine-gap alignment with clipping: the rust-bio aligner behind bio_align_utils::PairwiseAligner ----
+ * Replaces bio::alignment::pairwise::banded::Aligner::custom_with_matches as called at
+ * reference src/bio_align_utils.rs:170-188 (PairwiseAligner::align / align_with_matches).  Scoring follows
+ * bio::alignment::pairwise::Scoring: gap_open / gap_extend <= 0, match, mismatch, and the four clip penalties
+ * (SFC_BIO_MIN_SCORE = clipping disabled); e.g. new_merge_aligner (:104-112) is {0,-2,1,-3, MIN,MIN,0,0}.
+ * x = pattern (globally aligned unless x-clips are enabled), y = text.  The reference's k-mer band is not applied:
+ * the whole matrix is filled (same result whenever the band contains the optimal path). */
+#define SFC_BIO_MIN_SCORE (-858993459)
+typedef struct {
+  int32_t gap_open, gap_extend, match, mismatch;
+  int32_t xclip_prefix, xclip_suffix, yclip_prefix, yclip_suffix;
+} sfc_bio_scoring;
+enum { SFC_BIO_MATCH = 0, SFC_BIO_SUBST = 1, SFC_BIO_INS = 2, SFC_BIO_DEL = 3, SFC_BIO_XCLIP = 4, SFC_BIO_YCLIP = 5 };
+/* pairs: pattern_off/len = x, text_off/len = y (byte offsets into seq_arena; the free-end and flag fields are ignored).
+ * scores[n], status[n] (0 = ok, -6 = pair does not fit the device workspace), bounds[4n] = xstart, xend, ystart, yend
+ * (rust-bio Alignment fields), ops: run-length words (len << 3 | SFC_BIO_*) in alignment order, clip operations
+ * carry the clipped length; ops_off[n+1] delimits each pair's words.  ops / ops_off may be NULL (score only). */
+int sfc_bio_align_batch(sfc_ctx*, const sfc_bio_scoring*, const uint8_t* seq_arena, size_t arena_len, const sfc_pair* pairs,
+                        size_t n_pairs, int32_t* scores, int32_t* status, int32_t* bounds, uint32_t* ops, size_t ops_cap,
+                        uint64_t* ops_off);
+
 #ifdef __cplusplus
 }
 #endif

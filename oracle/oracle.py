@@ -39,8 +39,26 @@ CONSENSUS = Penalties(0, -1, 3, 0, 2, 0, 0)
 LARGE_INDEL = Penalties(1, -1, 3, 1, 2, 60, 0)
 
 
+BIO_MIN_SCORE = -858993459
+
+
+class BioScoring(C.Structure):
+    """rust-bio Scoring::from_scores(gap_open, gap_extend, match, mismatch) + clip penalties (MIN_SCORE = disabled)."""
+    _fields_ = [(n, C.c_int32) for n in ("gap_open", "gap_extend", "match", "mismatch", "xclip_prefix", "xclip_suffix",
+                                         "yclip_prefix", "yclip_suffix")]
+
+
+class BioResult(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("score", "xstart", "xend", "ystart", "yend")]
+
+
+def bio_scoring(gap_open, gap_extend, match, mismatch, xclip_prefix=BIO_MIN_SCORE, xclip_suffix=BIO_MIN_SCORE,
+                yclip_prefix=BIO_MIN_SCORE, yclip_suffix=BIO_MIN_SCORE) -> BioScoring:
+    return BioScoring(gap_open, gap_extend, match, mismatch, xclip_prefix, xclip_suffix, yclip_prefix, yclip_suffix)
+
+
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("wfa_oracle.c", "dp_verify.c", "wfa_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("wfa_oracle.c", "dp_verify.c", "bio_oracle.c", "wfa_oracle.h")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
     return _SO
@@ -71,6 +89,9 @@ def lib():
         L.ora_max_threads.restype = C.c_int
         L.dp_min_penalty.argtypes = [C.c_int] * 6 + [u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.dp_min_penalty.restype = C.c_int
+        L.bio_custom_align.argtypes = [C.POINTER(BioScoring), u8p, C.c_int, u8p, C.c_int, C.POINTER(BioResult),
+                                       C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_int)]
+        L.bio_custom_align.restype = C.c_int
         _lib = L
     return _lib
 
@@ -183,3 +204,21 @@ def dp_min_penalty(pen: Penalties, pattern: bytes, text: bytes, pbf: int, pef: i
 
 def max_threads() -> int:
     return lib().ora_max_threads()
+
+
+BIO_OPS = ("Match", "Subst", "Ins", "Del", "Xclip", "Yclip")
+
+
+def bio_custom_align(scoring: BioScoring, x: bytes, y: bytes):
+    """rust-bio Aligner::custom(x = pattern, y = text) restated (oracle/bio_oracle.c).
+    Returns (score, xstart, xend, ystart, yend, [(op name, len)]) with one entry per operation."""
+    L = lib()
+    cap = 2 * (len(x) + len(y)) + 16
+    ops = (C.c_uint32 * cap)()
+    n_ops = C.c_int(0)
+    res = BioResult()
+    rc = L.bio_custom_align(C.byref(scoring), _buf(x), len(x), _buf(y), len(y), C.byref(res), ops, cap, C.byref(n_ops))
+    if rc != 0:
+        raise RuntimeError(f"bio_custom_align rc={rc}")
+    out = [(BIO_OPS[w & 7], w >> 3) for w in ops[:n_ops.value]]
+    return res.score, res.xstart, res.xend, res.ystart, res.yend, out

@@ -28,6 +28,12 @@ class Penalties(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("metric", "match", "mismatch", "gap_open1", "gap_ext1", "gap_open2", "gap_ext2")]
 
 
+class BioScoring(C.Structure):
+    """sfc_bio_scoring: rust-bio Scoring (gap_open, gap_extend, match, mismatch) + the four clip penalties."""
+    _fields_ = [(n, C.c_int32) for n in ("gap_open", "gap_extend", "match", "mismatch", "xclip_prefix", "xclip_suffix",
+                                         "yclip_prefix", "yclip_suffix")]
+
+
 class BatchStats(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("pack_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("cells", C.c_uint64), ("launches", C.c_uint32),
@@ -42,6 +48,7 @@ EXPORTS = [
     "sfc_aligner_new_consensus", "sfc_aligner_new_large_indel", "sfc_aligner_free", "sfc_aligner_set_text",
     "sfc_aligner_align", "sfc_measure_int_peak", "sfc_estimate_pair_work", "sfc_shard_plan", "sfc_multi_create", "sfc_multi_destroy",
     "sfc_multi_device_count", "sfc_multi_last_error", "sfc_multi_align_batch", "sfc_multi_last_kernel_ms",
+    "sfc_bio_align_batch",
 ]
 
 
@@ -104,6 +111,8 @@ def lib():
     L.sfc_multi_align_batch.argtypes = [vp, C.POINTER(Penalties), u8p, C.c_size_t, vp, C.c_size_t, vp, C.c_int, i32p, i32p, u32p,
                                         C.c_size_t, u64p]
     L.sfc_multi_last_kernel_ms.argtypes = [vp, vp]
+    L.sfc_bio_align_batch.argtypes = [vp, C.POINTER(BioScoring), u8p, C.c_size_t, vp, C.c_size_t, i32p, i32p, i32p, u32p,
+                                      C.c_size_t, u64p]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("sfc_abi_version", "sfc_device_count"):

@@ -106,6 +106,27 @@ class AlignContext:
         self.run(pen, want_cigar)
         return self.download()
 
+    def bio_align_batch(self, scoring, arena: np.ndarray, pairs: np.ndarray, want_ops: bool = True):
+        """sfc_bio_align_batch: rust-bio style affine alignment with clipping (K4).  pairs: PAIR_DTYPE rows whose
+        pattern_* = x and text_* = y.  Returns scores, status, bounds[n,4] (xstart, xend, ystart, yend), ops, ops_off."""
+        assert arena.dtype == np.uint8 and arena.flags.c_contiguous
+        assert pairs.dtype == PAIR_DTYPE and pairs.flags.c_contiguous
+        n = len(pairs)
+        scores = np.zeros(n, np.int32)
+        status = np.zeros(n, np.int32)
+        bounds = np.zeros((n, 4), np.int32)
+        if want_ops:
+            cap = int(pairs["pattern_len"].astype(np.int64).sum() + pairs["text_len"].astype(np.int64).sum()) + 4 * n
+            ops = np.zeros(cap, np.uint32)
+            ops_off = np.zeros(n + 1, np.uint64)
+            self._check(self._L.sfc_bio_align_batch(self._h, C.byref(scoring), arena.ctypes.data, arena.size, pairs.ctypes.data, n,
+                                                    scores.ctypes.data, status.ctypes.data, bounds.ctypes.data, ops.ctypes.data,
+                                                    cap, ops_off.ctypes.data))
+            return scores, status, bounds, ops, ops_off
+        self._check(self._L.sfc_bio_align_batch(self._h, C.byref(scoring), arena.ctypes.data, arena.size, pairs.ctypes.data, n,
+                                                scores.ctypes.data, status.ctypes.data, bounds.ctypes.data, None, 0, None))
+        return scores, status, bounds, None, None
+
     def measure_int_peak(self):
         g, m = C.c_double(), C.c_double()
         self._check(self._L.sfc_measure_int_peak(self._h, C.byref(g), C.byref(m)))

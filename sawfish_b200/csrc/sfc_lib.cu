@@ -20,6 +20,7 @@
 
 #include "sfc_device.cuh"
 #include "sfc_k_align.cuh"
+#include "sfc_k_bio.cuh"
 #include "sfc_k_pack.cuh"
 #include "sfc_k_score.cuh"
 
@@ -50,6 +51,7 @@ struct sfc_ctx {
   size_t ws_limit = 0;
   // device buffers
   DevBuf d_arena, d_nib, d_seqs, d_seqwoff, d_pairs, d_order, d_scores, d_status, d_misc, d_pool, d_outoff, d_outlen, d_ws;
+  DevBuf d_b_arena, d_b_pairs, d_b_out, d_b_pool;  // K4 (bio aligner) staging; the slabs reuse d_ws
   // batch state
   size_t n_pairs = 0;
   bool uploaded = false, ran = false;
@@ -239,7 +241,8 @@ extern "C" void sfc_destroy(sfc_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->d_arena, &c->d_nib, &c->d_seqs, &c->d_seqwoff, &c->d_pairs, &c->d_order, &c->d_scores, &c->d_status,
-                    &c->d_misc, &c->d_pool, &c->d_outoff, &c->d_outlen, &c->d_ws})
+                    &c->d_misc, &c->d_pool, &c->d_outoff, &c->d_outlen, &c->d_ws, &c->d_b_arena, &c->d_b_pairs, &c->d_b_out,
+                    &c->d_b_pool})
     release(*b);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->job_ev) if (e) cudaEventDestroy(e);
@@ -1181,5 +1184,94 @@ extern "C" int sfc_measure_int_peak(sfc_ctx* c, double* gops, double* mhz_est) {
   release(out);
   *gops = best;
   if (mhz_est) *mhz_est = best * 1e3 / ((double)c->sm_count * 64.0);  // assuming 64 INT32 lanes/SM/clk
+  return SFC_OK;
+}
+
+// ============================================================================ K4: rust-bio style aligner
+extern "C" int sfc_bio_align_batch(sfc_ctx* c, const sfc_bio_scoring* sco, const uint8_t* arena, size_t arena_len,
+                                   const sfc_pair* pairs, size_t n, int32_t* scores, int32_t* status, int32_t* bounds,
+                                   uint32_t* ops, size_t ops_cap, uint64_t* ops_off) {
+  if (!c) return SFC_ERR_INVALID;
+  if (!sco || !arena || !pairs || n == 0 || n > 0x7FFFFFF0u || !scores || !status || !bounds)
+    return fail(c, SFC_ERR_INVALID, "null/empty batch");
+  if (sco->gap_open > 0 || sco->gap_extend > 0) return fail(c, SFC_ERR_INVALID, "gap penalties must be <= 0");
+  if ((ops == nullptr) != (ops_off == nullptr)) return fail(c, SFC_ERR_INVALID, "ops and ops_off go together");
+  CU(cudaSetDevice(c->device));
+  std::vector<K4Pair> hp(n);
+  size_t max_need = 0, tot_ops = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const sfc_pair& p = pairs[i];
+    if (p.pattern_len == 0 || p.text_len == 0) return fail(c, SFC_ERR_INVALID, "pair %zu: empty sequence", i);  // assert!(!text.is_empty())
+    if (p.pattern_off + p.pattern_len > arena_len || p.text_off + p.text_len > arena_len)
+      return fail(c, SFC_ERR_INVALID, "pair %zu outside the arena", i);
+    if (p.pattern_len > 1000000u || p.text_len > 1000000u) return fail(c, SFC_ERR_UNSUPPORTED, "pair %zu: sequence too long", i);
+    hp[i] = K4Pair{p.pattern_off, p.text_off, (int)p.pattern_len, (int)p.text_len};
+    max_need = std::max(max_need, k4_slab_need(hp[i].m, hp[i].n));
+    tot_ops += (size_t)p.pattern_len + p.text_len + 4;
+  }
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  size_t avail = (size_t)((double)(free_b + c->d_ws.cap) * 0.8);
+  if (c->ws_limit && avail > c->ws_limit) avail = c->ws_limit;
+  if (max_need > avail) return fail(c, SFC_ERR_OOM, "device workspace too small: need %zu B for one pair", max_need);
+  const size_t slab = (max_need + 255) & ~(size_t)255;
+  size_t ctas = std::min<size_t>(std::min<size_t>(n, (size_t)c->sm_count * 2), std::max<size_t>(1, avail / slab));
+  int rc;
+  if ((rc = ensure(c, c->d_ws, slab * ctas))) return rc;
+  if ((rc = ensure(c, c->d_b_arena, arena_len))) return rc;
+  if ((rc = ensure(c, c->d_b_pairs, n * sizeof(K4Pair)))) return rc;
+  // out block: scores[n] status[n] bounds[4n] out_len[n] (int32) | out_off[n] (u64) | counter, pool_used
+  const size_t out_i32 = 7 * n, out_bytes = ((out_i32 * 4 + 15) & ~(size_t)15) + 8 * n + 32;
+  if ((rc = ensure(c, c->d_b_out, out_bytes))) return rc;
+  const size_t pool_cap = std::min<size_t>(tot_ops, (size_t)1 << 31);
+  if ((rc = ensure(c, c->d_b_pool, pool_cap * 4))) return rc;
+  unsigned char* ob = (unsigned char*)c->d_b_out.p;
+  int32_t* d_scores = (int32_t*)ob;
+  int32_t* d_status = d_scores + n;
+  int32_t* d_bounds = d_status + n;
+  uint32_t* d_outlen = (uint32_t*)(d_bounds + 4 * n);
+  unsigned long long* d_outoff = (unsigned long long*)(ob + ((out_i32 * 4 + 15) & ~(size_t)15));
+  unsigned long long* d_tail = d_outoff + n;  // [0] pool_used, [1] work counter (low 32 bits)
+  CU(cudaMemcpyAsync(c->d_b_arena.p, arena, arena_len, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_b_pairs.p, hp.data(), n * sizeof(K4Pair), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(d_tail, 0, 16, c->stream));
+  K4Params P;
+  P.arena = (const uint8_t*)c->d_b_arena.p;
+  P.pairs = (const K4Pair*)c->d_b_pairs.p;
+  P.n = (uint32_t)n;
+  P.counter = (uint32_t*)(d_tail + 1);
+  P.sc = K4Scoring{sco->gap_open, sco->gap_extend, sco->match, sco->mismatch, sco->xclip_prefix, sco->xclip_suffix,
+                   sco->yclip_prefix, sco->yclip_suffix};
+  P.slabs = (unsigned char*)c->d_ws.p;
+  P.slab_bytes = slab;
+  P.scores = d_scores; P.status = d_status; P.bounds = d_bounds;
+  P.pool = (uint32_t*)c->d_b_pool.p; P.pool_cap = pool_cap; P.pool_used = d_tail;
+  P.out_off = d_outoff; P.out_len = d_outlen;
+  k4_bio_align<<<(unsigned)ctas, 256, 0, c->stream>>>(P);
+  CU(cudaGetLastError());
+  c->stats.launches++;
+  CU(cudaMemcpyAsync(scores, d_scores, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(bounds, d_bounds, n * 16, cudaMemcpyDeviceToHost, c->stream));
+  if (ops_off) {
+    std::vector<uint32_t> h_len(n);
+    std::vector<unsigned long long> h_off(n);
+    CU(cudaMemcpyAsync(h_len.data(), d_outlen, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h_off.data(), d_outoff, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    size_t total = 0;
+    for (size_t i = 0; i < n; ++i) total += (status[i] == 0) ? h_len[i] : 0;
+    if (total > ops_cap) return fail(c, SFC_ERR_CAPACITY, "ops_cap %zu < %zu words", ops_cap, total);
+    size_t pos = 0;
+    for (size_t i = 0; i < n; ++i) {
+      ops_off[i] = pos;
+      if (status[i] == 0 && h_len[i]) {
+        CU(cudaMemcpyAsync(ops + pos, (uint32_t*)c->d_b_pool.p + h_off[i], (size_t)h_len[i] * 4, cudaMemcpyDeviceToHost, c->stream));
+        pos += h_len[i];
+      }
+    }
+    ops_off[n] = pos;
+  }
+  CU(cudaStreamSynchronize(c->stream));
   return SFC_OK;
 }

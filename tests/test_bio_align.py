@@ -1,0 +1,191 @@
+"""rust-bio style aligner (bio_align_utils): oracle vs the reference's known answers and an independent definition
+(not gpu), CUDA K4 vs oracle and the same known answers through the host mirror (gpu).
+
+Known answers: reference src/bio_align_utils.rs:291-403 (nine of them, four aligner flavours)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+TEXT = b"AACTGTATAA"
+
+
+def rle(ops):
+    out = []
+    for name, n in ops:
+        if out and out[-1][0] == name and name not in ("Xclip", "Yclip"):
+            out[-1] = (name, out[-1][1] + n)
+        else:
+            out.append((name, n))
+    return out
+
+
+def cigar_of(ops):
+    m = {"Del": "D", "Ins": "I", "Match": "=", "Subst": "X", "Xclip": "S"}
+    return "".join(f"{n}{m[name]}" for name, n in rle(ops) if name != "Yclip")
+
+
+def scorings():
+    w = dict(gap_open=-1, gap_extend=-1, match=1, mismatch=-3)  # get_test_weights, :281-288
+    return {
+        "merge": O.bio_scoring(0, -2, 1, -3, yclip_prefix=0, yclip_suffix=0),
+        "glocal": O.bio_scoring(**w, yclip_prefix=0, yclip_suffix=0),
+        "suffix": O.bio_scoring(**w, yclip_prefix=0, xclip_suffix=0),
+        "prefix": O.bio_scoring(**w, yclip_suffix=0, xclip_prefix=0),
+    }
+
+
+KNOWN = [  # flavour, pattern, score, (ref_offset, cigar) or None when the reference only checks the score
+    ("merge", b"ACTTAT", 4, (1, "3=1D3=")),
+    ("glocal", b"CTGAATA", 3, (2, "3=1X3=")),
+    ("glocal", b"CCGAACT", 0, None),
+    ("glocal", b"ACTGATA", 5, (1, "4=1D3=")),
+    ("suffix", b"ATAACCG", 4, (6, "4=3S")),
+    ("suffix", b"CCGAACT", 0, None),
+    ("prefix", b"CCGAACT", 4, (0, "3S4=")),
+    ("prefix", b"ATAACCG", 1, None),
+]
+
+
+@pytest.mark.parametrize("flavour,pattern,score,aln", KNOWN)
+def test_oracle_reproduces_reference_known_answers(flavour, pattern, score, aln):
+    s, xs, xe, ys, ye, ops = O.bio_custom_align(scorings()[flavour], pattern, TEXT)
+    assert s == score
+    if aln is not None:
+        assert (ys, cigar_of(ops)) == aln
+
+
+def global_affine(sc, x, y):
+    """Plain Gotoh global alignment score (gap of length L costs open + L * extend), independent of the oracle's code."""
+    NEG = -10**9
+    m, n = len(x), len(y)
+    S = [[NEG] * (n + 1) for _ in range(m + 1)]
+    I = [[NEG] * (n + 1) for _ in range(m + 1)]
+    D = [[NEG] * (n + 1) for _ in range(m + 1)]
+    S[0][0] = 0
+    for i in range(m + 1):
+        for j in range(n + 1):
+            if i > 0:
+                I[i][j] = max(I[i - 1][j] + sc.gap_extend, S[i - 1][j] + sc.gap_open + sc.gap_extend)
+            if j > 0:
+                D[i][j] = max(D[i][j - 1] + sc.gap_extend, S[i][j - 1] + sc.gap_open + sc.gap_extend)
+            if i > 0 and j > 0:
+                S[i][j] = S[i - 1][j - 1] + (sc.match if x[i - 1] == y[j - 1] else sc.mismatch)
+            if i or j:
+                S[i][j] = max(S[i][j], I[i][j], D[i][j])
+    return S[m][n]
+
+
+def test_oracle_glocal_score_is_best_text_substring():
+    """yclip(0): pattern global, text local == max over text substrings of the global affine score."""
+    rng = np.random.default_rng(5)
+    sc = scorings()["merge"]
+    for _ in range(12):
+        x = bytes(rng.choice(list(b"ACGT"), int(rng.integers(1, 8))))
+        y = bytes(rng.choice(list(b"ACGT"), int(rng.integers(1, 10))))
+        want = max(global_affine(sc, x, y[a:b]) for a in range(len(y) + 1) for b in range(a, len(y) + 1))
+        got = O.bio_custom_align(sc, x, y)[0]
+        assert got == want, (x, y, got, want)
+
+
+def test_oracle_operations_replay_to_the_score():
+    rng = np.random.default_rng(6)
+    for name, sc in scorings().items():
+        for _ in range(30):
+            base = rng.choice(list(b"ACGT"), int(rng.integers(5, 60)))
+            x = bytes(base[int(rng.integers(0, 3)):])
+            y = bytes(rng.choice(list(b"ACGT"), int(rng.integers(0, 6)))) + bytes(base) + bytes(rng.choice(list(b"ACGT"), 3))
+            s, xs, xe, ys, ye, ops = O.bio_custom_align(sc, x, y)
+            i, j, tot, prev = 0, 0, 0, None
+            for op, n in ops:
+                if op in ("Match", "Subst"):
+                    assert (x[i] == y[j]) == (op == "Match")
+                    tot += sc.match if op == "Match" else sc.mismatch
+                    i += 1; j += 1
+                elif op == "Ins":
+                    tot += sc.gap_extend + (sc.gap_open if prev != "Ins" else 0); i += 1
+                elif op == "Del":
+                    tot += sc.gap_extend + (sc.gap_open if prev != "Del" else 0); j += 1
+                elif op == "Xclip":
+                    tot += sc.xclip_prefix if i == 0 else sc.xclip_suffix; i += n
+                else:
+                    tot += sc.yclip_prefix if j == 0 else sc.yclip_suffix; j += n
+                prev = op
+            assert (i, j, tot) == (len(x), len(y), s), (name, x, y, ops)
+
+
+# ---------------------------------------------------------------------------------------------------------- GPU
+def _to_gpu_scoring(sc):
+    from sawfish_b200._lib import BioScoring
+    return BioScoring(sc.gap_open, sc.gap_extend, sc.match, sc.mismatch, sc.xclip_prefix, sc.xclip_suffix, sc.yclip_prefix,
+                      sc.yclip_suffix)
+
+
+@pytest.mark.gpu
+def test_host_mirror_replays_reference_tests():
+    """The reference's own unit tests (src/bio_align_utils.rs:291-403) through the CUDA path and the host mirror."""
+    from sawfish_b200.batch import AlignContext
+    from sawfish_b200.bio_align_utils import AlignmentWeights, OverlapPairwiseAligner, PairwiseAligner, scoring_from_scores
+    from sawfish_b200.simple_alignment import cigar_to_string
+    ctx = AlignContext(0)
+    w = AlignmentWeights(match_=1, mismatch=-3, gap_open=-1, gap_extend=-1)
+    sc = scoring_from_scores(w.gap_open, w.gap_extend, w.match_, w.mismatch)
+    makers = {"merge": lambda: PairwiseAligner.new_merge_aligner(ctx), "glocal": lambda: PairwiseAligner.new_glocal_aligner(ctx, w),
+              "suffix": lambda: PairwiseAligner.new_pattern_suffix_aligner(ctx, sc, 20, 10),
+              "prefix": lambda: PairwiseAligner.new_pattern_prefix_aligner(ctx, sc, 20, 10)}
+    for flavour, pattern, score, aln in KNOWN:
+        a = makers[flavour]()
+        assert a.align(TEXT, pattern) == score
+        if aln is not None:
+            got = a.get_last_alignment()
+            assert (got.ref_offset, cigar_to_string(got.cigar)) == aln
+    ov = OverlapPairwiseAligner.new_aligner(ctx, w)  # test_overlap_aligner, :381-402
+    assert ov.align(TEXT, b"ATAACCG") == 4
+    got = ov.get_last_alignment()
+    assert (got.ref_offset, cigar_to_string(got.cigar)) == (6, "4=3S")
+    assert ov.align(TEXT, b"CCGAACT") == 4
+    got = ov.get_last_alignment()
+    assert (got.ref_offset, cigar_to_string(got.cigar)) == (0, "3S4=")
+
+
+@pytest.mark.gpu
+def test_k4_matches_oracle_on_random_pairs():
+    from sawfish_b200.batch import AlignContext, PAIR_DTYPE
+    ctx = AlignContext(0)
+    rng = np.random.default_rng(11)
+    acgt = np.frombuffer(b"ACGTN", np.uint8)
+    for name, sc in scorings().items():
+        seqs, rows, off = [], [], 0
+        cases = []
+        for q in range(60):
+            L = int(rng.integers(2, 700 if q < 50 else 3000))
+            base = acgt[rng.integers(0, 4, L)]
+            x = base.copy()
+            for _ in range(int(rng.integers(0, 6))):  # a few edits
+                pos = int(rng.integers(0, len(x)))
+                kind = int(rng.integers(0, 3))
+                if kind == 0:
+                    x[pos] = acgt[int(rng.integers(0, 5))]
+                elif kind == 1 and len(x) > 40:
+                    x = np.delete(x, slice(pos, pos + int(rng.integers(1, 30))))
+                else:
+                    x = np.insert(x, pos, acgt[rng.integers(0, 4, int(rng.integers(1, 30)))])
+            if rng.random() < 0.5 and len(x) > 12:  # pattern covers only part of the text's core
+                x = x[int(rng.integers(0, len(x) // 3)):len(x) - int(rng.integers(0, len(x) // 3))]
+            y = np.concatenate([acgt[rng.integers(0, 4, int(rng.integers(0, 50)))], base, acgt[rng.integers(0, 4, int(rng.integers(0, 50)))]])
+            cases.append((x.tobytes(), y.tobytes()))
+            rows.append((off, off + len(x), len(x), len(y), 0, 0, 0, 0, 0))
+            seqs += [x, y]
+            off += len(x) + len(y)
+        arena = np.concatenate(seqs)
+        tab = np.array(rows, dtype=PAIR_DTYPE)
+        scores, status, bounds, ops, ops_off = ctx.bio_align_batch(_to_gpu_scoring(sc), arena, tab, True)
+        assert (status == 0).all()
+        for i, (x, y) in enumerate(cases):
+            s, xs, xe, ys, ye, o_ops = O.bio_custom_align(sc, x, y)
+            assert scores[i] == s, (name, i, len(x), len(y))
+            assert tuple(bounds[i]) == (xs, xe, ys, ye), (name, i)
+            want = rle(o_ops)
+            names = ("Match", "Subst", "Ins", "Del", "Xclip", "Yclip")
+            got = [(names[int(w) & 7], int(w) >> 3) for w in ops[int(ops_off[i]):int(ops_off[i + 1])]]
+            assert got == want, (name, i, got[:6], want[:6])
