@@ -184,6 +184,15 @@ int sfc_bio_align_batch(sfc_ctx*, const sfc_bio_scoring*, const uint8_t* seq_are
                         size_t n_pairs, int32_t* scores, int32_t* status, int32_t* bounds, uint32_t* ops, size_t ops_cap,
                         uint64_t* ops_off);
 
+/* Score-only form of the same aligner (K5: no traceback matrix, one warp per pair, rows in registers).  This is what
+ * the merge aligner's callers consume: reference src/joint_call/merge_haplotypes/single_region/merge_pools.rs:253-257
+ * and multi_region/merge_pools.rs:57 keep only `aligner.align(base, query)`'s score (norm score >= 0.97).
+ * scores[i] is identical to what sfc_bio_align_batch returns for the pair.  Scorings with an enabled x-suffix clip
+ * (new_pattern_suffix_aligner, src/bio_align_utils.rs:139-146) are served by the K4 kernel behind the same call.
+ * sfc_batch_get_stats afterwards reports this call (cells = sum |x|*|y|). */
+int sfc_bio_score_batch(sfc_ctx*, const sfc_bio_scoring*, const uint8_t* seq_arena, size_t arena_len, const sfc_pair* pairs,
+                        size_t n_pairs, int32_t* scores, int32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,7 +48,7 @@ EXPORTS = [
     "sfc_aligner_new_consensus", "sfc_aligner_new_large_indel", "sfc_aligner_free", "sfc_aligner_set_text",
     "sfc_aligner_align", "sfc_measure_int_peak", "sfc_estimate_pair_work", "sfc_shard_plan", "sfc_multi_create", "sfc_multi_destroy",
     "sfc_multi_device_count", "sfc_multi_last_error", "sfc_multi_align_batch", "sfc_multi_last_kernel_ms",
-    "sfc_bio_align_batch",
+    "sfc_bio_align_batch", "sfc_bio_score_batch",
 ]
 
 
@@ -113,6 +113,7 @@ def lib():
     L.sfc_multi_last_kernel_ms.argtypes = [vp, vp]
     L.sfc_bio_align_batch.argtypes = [vp, C.POINTER(BioScoring), u8p, C.c_size_t, vp, C.c_size_t, i32p, i32p, i32p, u32p,
                                       C.c_size_t, u64p]
+    L.sfc_bio_score_batch.argtypes = [vp, C.POINTER(BioScoring), u8p, C.c_size_t, vp, C.c_size_t, i32p, i32p]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("sfc_abi_version", "sfc_device_count"):

@@ -127,6 +127,17 @@ class AlignContext:
                                                 scores.ctypes.data, status.ctypes.data, bounds.ctypes.data, None, 0, None))
         return scores, status, bounds, None, None
 
+    def bio_score_batch(self, scoring, arena: np.ndarray, pairs: np.ndarray):
+        """sfc_bio_score_batch: the same aligner, score only (K5).  Returns scores, status."""
+        assert arena.dtype == np.uint8 and arena.flags.c_contiguous
+        assert pairs.dtype == PAIR_DTYPE and pairs.flags.c_contiguous
+        n = len(pairs)
+        scores = np.zeros(n, np.int32)
+        status = np.zeros(n, np.int32)
+        self._check(self._L.sfc_bio_score_batch(self._h, C.byref(scoring), arena.ctypes.data, arena.size, pairs.ctypes.data, n,
+                                                scores.ctypes.data, status.ctypes.data))
+        return scores, status
+
     def measure_int_peak(self):
         g, m = C.c_double(), C.c_double()
         self._check(self._L.sfc_measure_int_peak(self._h, C.byref(g), C.byref(m)))

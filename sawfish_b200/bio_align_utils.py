@@ -128,6 +128,21 @@ class PairwiseAligner:
             out.append(BioAlignment(int(scores[i]), int(bounds[i, 0]), int(bounds[i, 1]), int(bounds[i, 2]), int(bounds[i, 3]), oplist))
         return out
 
+    def score_batch(self, pairs: Sequence[Tuple[bytes, bytes]]) -> List[int]:
+        """Scores only, for callers that never look at the alignment (the merge aligner's: merge_pools.rs:253-257).
+        pairs: (text, pattern) in the reference's argument order.  One K5 launch (sfc_bio_score_batch)."""
+        chunks, rows, off = [], [], 0
+        for text, pattern in pairs:
+            assert len(text) > 0 and len(pattern) > 0  # :177-178
+            t = np.frombuffer(bytes(text), np.uint8)
+            p = np.frombuffer(bytes(pattern), np.uint8)
+            rows.append((off + len(t), off, len(p), len(t), 0, 0, 0, 0, 0))
+            chunks += [t, p]
+            off += len(t) + len(p)
+        scores, status = self.ctx.bio_score_batch(self.scoring, np.concatenate(chunks), np.array(rows, dtype=PAIR_DTYPE))
+        assert (status == 0).all(), f"K5 status {status[status != 0][:4]}"
+        return [int(v) for v in scores]
+
     def align(self, text: bytes, pattern: bytes) -> int:  # :168-172
         self.alignment = self.align_batch([(text, pattern)])[0]
         return self.alignment.score
@@ -161,3 +176,17 @@ class OverlapPairwiseAligner:
 
     def get_last_alignment(self) -> Optional[SimpleAlignment]:
         return (self.pattern_suffix_aligner if self.is_suffix else self.pattern_prefix_aligner).get_last_alignment()
+
+
+def test_for_duplicate_haplotypes_with_alignment(ctx, base_query_pairs: Sequence[Tuple[bytes, bytes]],
+                                                 min_merge_norm_score: float = 0.97) -> List[bool]:
+    """Batched form of the alignment test joint-call uses to merge duplicate haplotypes across samples
+    (src/joint_call/merge_haplotypes/single_region/merge_pools.rs:214-272): the query's high-quality range is aligned
+    globally against the base contig (text local) with the merge aligner, the score is normalised by the query length,
+    and the pair is a duplicate when that is >= 0.97.  base_query_pairs: (base_contig, query_contig[hq_range])."""
+    aligner = PairwiseAligner.new_merge_aligner(ctx)
+    scores = aligner.score_batch(base_query_pairs)
+    return [s / len(q) >= min_merge_norm_score for s, (_b, q) in zip(scores, base_query_pairs)]
+
+
+test_for_duplicate_haplotypes_with_alignment.__test__ = False  # a reference function name, not a pytest case

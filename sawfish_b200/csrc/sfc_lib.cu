@@ -21,6 +21,7 @@
 #include "sfc_device.cuh"
 #include "sfc_k_align.cuh"
 #include "sfc_k_bio.cuh"
+#include "sfc_k_bio_score.cuh"
 #include "sfc_k_pack.cuh"
 #include "sfc_k_score.cuh"
 
@@ -1273,5 +1274,94 @@ extern "C" int sfc_bio_align_batch(sfc_ctx* c, const sfc_bio_scoring* sco, const
     ops_off[n] = pos;
   }
   CU(cudaStreamSynchronize(c->stream));
+  return SFC_OK;
+}
+
+// ============================================================================ K5: rust-bio style aligner, score only
+extern "C" int sfc_bio_score_batch(sfc_ctx* c, const sfc_bio_scoring* sco, const uint8_t* arena, size_t arena_len,
+                                   const sfc_pair* pairs, size_t n, int32_t* scores, int32_t* status) {
+  if (!c) return SFC_ERR_INVALID;
+  if (!sco || !arena || !pairs || n == 0 || n > 0x7FFFFFF0u || !scores || !status) return fail(c, SFC_ERR_INVALID, "null/empty batch");
+  if (sco->gap_open > 0 || sco->gap_extend > 0) return fail(c, SFC_ERR_INVALID, "gap penalties must be <= 0");
+  const bool xs_on = sco->xclip_suffix > K4_MIN_SCORE / 2;
+  if (xs_on || sco->xclip_prefix > 0 || sco->yclip_prefix > 0 || sco->yclip_suffix > 0) {
+    // x-suffix clipping (new_pattern_suffix_aligner) needs the per-column maximum K4 keeps: same scores, slower kernel
+    std::vector<int32_t> bounds(4 * n);
+    return sfc_bio_align_batch(c, sco, arena, arena_len, pairs, n, scores, status, bounds.data(), nullptr, 0, nullptr);
+  }
+  CU(cudaSetDevice(c->device));
+  std::vector<K4Pair> hp(n);
+  std::vector<uint32_t> order(n);
+  size_t max_n = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const sfc_pair& p = pairs[i];
+    if (p.pattern_len == 0 || p.text_len == 0) return fail(c, SFC_ERR_INVALID, "pair %zu: empty sequence", i);  // assert!(!text.is_empty())
+    if (p.pattern_off + p.pattern_len > arena_len || p.text_off + p.text_len > arena_len)
+      return fail(c, SFC_ERR_INVALID, "pair %zu outside the arena", i);
+    if (p.pattern_len > 1000000u || p.text_len > 1000000u) return fail(c, SFC_ERR_UNSUPPORTED, "pair %zu: sequence too long", i);
+    hp[i] = K4Pair{p.pattern_off, p.text_off, (int)p.pattern_len, (int)p.text_len};
+    max_n = std::max<size_t>(max_n, p.text_len);
+    order[i] = (uint32_t)i;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    return (uint64_t)hp[a].m * (uint64_t)hp[a].n > (uint64_t)hp[b].m * (uint64_t)hp[b].n;
+  });
+  const size_t stride = ((max_n + 1 + 31) & ~(size_t)31) + 32;
+  const size_t per_cta = (size_t)K5_NBUF * stride * sizeof(int2);
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  size_t avail = (size_t)((double)(free_b + c->d_ws.cap) * 0.8);
+  if (c->ws_limit && avail > c->ws_limit) avail = c->ws_limit;
+  if (per_cta > avail) return fail(c, SFC_ERR_OOM, "device workspace too small: need %zu B for one pair", per_cta);
+  const size_t ctas = std::min<size_t>(std::min<size_t>(n, (size_t)c->sm_count * 4), avail / per_cta);
+  int rc;
+  if ((rc = ensure(c, c->d_ws, per_cta * ctas))) return rc;
+  if ((rc = ensure(c, c->d_b_arena, arena_len))) return rc;
+  if ((rc = ensure(c, c->d_b_pairs, n * sizeof(K4Pair)))) return rc;
+  // out block: scores[n] status[n] order[n] | cells (u64), counter
+  const size_t out_bytes = ((3 * n * 4 + 15) & ~(size_t)15) + 32;
+  if ((rc = ensure(c, c->d_b_out, out_bytes))) return rc;
+  unsigned char* ob = (unsigned char*)c->d_b_out.p;
+  int32_t* d_scores = (int32_t*)ob;
+  int32_t* d_status = d_scores + n;
+  uint32_t* d_order = (uint32_t*)(d_status + n);
+  unsigned long long* d_tail = (unsigned long long*)(ob + ((3 * n * 4 + 15) & ~(size_t)15));  // [0] cells, [1] work counter
+  c->stats = sfc_batch_stats{};
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  CU(cudaMemcpyAsync(c->d_b_arena.p, arena, arena_len, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_b_pairs.p, hp.data(), n * sizeof(K4Pair), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_order, order.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(d_tail, 0, 16, c->stream));
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  K5Params P;
+  P.arena = (const uint8_t*)c->d_b_arena.p;
+  P.pairs = (const K4Pair*)c->d_b_pairs.p;
+  P.order = d_order;
+  P.n = (uint32_t)n;
+  P.counter = (uint32_t*)(d_tail + 1);
+  P.sc = K4Scoring{sco->gap_open, sco->gap_extend, sco->match, sco->mismatch, sco->xclip_prefix, sco->xclip_suffix,
+                   sco->yclip_prefix, sco->yclip_suffix};
+  P.bnd = (int2*)c->d_ws.p;
+  P.bnd_stride = stride;
+  P.scores = d_scores; P.status = d_status; P.cells = d_tail;
+  const unsigned grid = (unsigned)ctas;
+  if (sco->xclip_prefix > K4_MIN_SCORE / 2) k5_bio_score<true><<<grid, K5_WARPS * 32, 0, c->stream>>>(P);
+  else k5_bio_score<false><<<grid, K5_WARPS * 32, 0, c->stream>>>(P);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ev[2], c->stream));
+  unsigned long long h_cells = 0;
+  CU(cudaMemcpyAsync(scores, d_scores, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&h_cells, d_tail, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaEventRecord(c->ev[3], c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats.h2d_ms = ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->stats.kernel_ms = ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->stats.d2h_ms = ms;
+  c->stats.h2d_bytes = arena_len + n * (sizeof(K4Pair) + 4);
+  c->stats.d2h_bytes = n * 8 + 8;
+  c->stats.cells = h_cells;  // full-matrix cells |x| * |y|
+  c->stats.launches = 1;
   return SFC_OK;
 }

@@ -189,3 +189,104 @@ def test_k4_matches_oracle_on_random_pairs():
             names = ("Match", "Subst", "Ins", "Del", "Xclip", "Yclip")
             got = [(names[int(w) & 7], int(w) >> 3) for w in ops[int(ops_off[i]):int(ops_off[i + 1])]]
             assert got == want, (name, i, got[:6], want[:6])
+
+
+def _random_bio_cases(rng, n_small, n_large, max_large):
+    acgt = np.frombuffer(b"ACGTN", np.uint8)
+    cases = []
+    for q in range(n_small + n_large):
+        L = int(rng.integers(1, 700)) if q < n_small else int(rng.integers(700, max_large))
+        base = acgt[rng.integers(0, 4, L)]
+        x = base.copy()
+        for _ in range(int(rng.integers(0, 6))):
+            pos = int(rng.integers(0, len(x)))
+            kind = int(rng.integers(0, 3))
+            if kind == 0:
+                x[pos] = acgt[int(rng.integers(0, 5))]
+            elif kind == 1 and len(x) > 40:
+                x = np.delete(x, slice(pos, pos + int(rng.integers(1, 30))))
+            else:
+                x = np.insert(x, pos, acgt[rng.integers(0, 4, int(rng.integers(1, 30)))])
+        if rng.random() < 0.5 and len(x) > 12:
+            x = x[int(rng.integers(0, len(x) // 3)):len(x) - int(rng.integers(0, len(x) // 3))]
+        if rng.random() < 0.15:  # unrelated pattern: the score is dominated by clips / gaps
+            x = acgt[rng.integers(0, 4, int(rng.integers(1, 300)))]
+        y = np.concatenate([acgt[rng.integers(0, 4, int(rng.integers(0, 50)))], base, acgt[rng.integers(0, 4, int(rng.integers(0, 50)))]])
+        cases.append((x.tobytes(), y.tobytes()))
+    return cases
+
+
+def _pack_cases(cases):
+    from sawfish_b200.batch import PAIR_DTYPE
+    seqs, rows, off = [], [], 0
+    for x, y in cases:
+        rows.append((off, off + len(x), len(x), len(y), 0, 0, 0, 0, 0))
+        seqs += [np.frombuffer(x, np.uint8), np.frombuffer(y, np.uint8)]
+        off += len(x) + len(y)
+    return np.concatenate(seqs), np.array(rows, dtype=PAIR_DTYPE)
+
+
+@pytest.mark.gpu
+def test_k5_score_only_matches_oracle():
+    """sfc_bio_score_batch (K5, registers + shuffles, no traceback) == oracle score for every aligner flavour, on pairs
+    that span one lane, one band, several bands of each height (R = 4, 8, 16) and band boundaries."""
+    from sawfish_b200.batch import AlignContext
+    ctx = AlignContext(0)
+    rng = np.random.default_rng(23)
+    extra = {
+        "glocal_open": O.bio_scoring(-5, -1, 2, -4, yclip_prefix=0, yclip_suffix=0),
+        "global": O.bio_scoring(-3, -1, 1, -2),
+        "yprefix_only": O.bio_scoring(-1, -1, 1, -3, yclip_prefix=-2),
+        "clips_paid": O.bio_scoring(-2, -1, 1, -3, xclip_prefix=-4, yclip_prefix=-3, yclip_suffix=-5),
+    }
+    for name, sc in {**scorings(), **extra}.items():
+        cases = _random_bio_cases(rng, 70, 10, 2600)
+        for mlen in (1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257, 383, 384, 385, 511, 512, 513, 640, 641, 1025):
+            y = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(rng.integers(1, 900)))]
+            x = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, mlen)]
+            k = min(len(x), len(y))
+            if k > 4 and rng.random() < 0.7:
+                x[:k] = y[:k]
+            cases.append((x.tobytes(), y.tobytes()))
+        arena, tab = _pack_cases(cases)
+        scores, status = ctx.bio_score_batch(_to_gpu_scoring(sc), arena, tab)
+        assert (status == 0).all()
+        for i, (x, y) in enumerate(cases):
+            s = O.bio_custom_align(sc, x, y)[0]
+            assert scores[i] == s, (name, i, len(x), len(y), int(scores[i]), s)
+
+
+@pytest.mark.gpu
+def test_k5_agrees_with_k4_on_merge_shaped_pairs():
+    """Base contig x high-quality range of a near-identical contig (merge_pools.rs:214-272): K5 scores == K4 scores, and
+    the merge decision (norm score >= 0.97) through the host mirror."""
+    from sawfish_b200.batch import AlignContext
+    from sawfish_b200.bio_align_utils import PairwiseAligner, test_for_duplicate_haplotypes_with_alignment
+    ctx = AlignContext(0)
+    rng = np.random.default_rng(29)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    cases = []
+    for q in range(24):
+        L = int(rng.integers(600, 6000))
+        base = acgt[rng.integers(0, 4, L)]
+        qy = base[int(0.1 * L):int(0.9 * L)].copy()
+        n_edit = max(1, len(qy) // (200 if q % 3 else 20))  # every third query is too diverged to merge
+        for _e in range(n_edit):
+            pos = int(rng.integers(0, len(qy)))
+            kind = int(rng.integers(0, 3))
+            if kind == 0:
+                qy[pos] = acgt[int(rng.integers(0, 4))]
+            elif kind == 1:
+                qy = np.delete(qy, pos)
+            else:
+                qy = np.insert(qy, pos, acgt[int(rng.integers(0, 4))])
+        cases.append((qy.tobytes(), base.tobytes()))
+    ma = PairwiseAligner.new_merge_aligner(ctx)
+    arena, tab = _pack_cases(cases)
+    s5, st5 = ctx.bio_score_batch(ma.scoring, arena, tab)
+    s4, st4, _b, _o, _oo = ctx.bio_align_batch(ma.scoring, arena, tab, False)
+    assert (st5 == 0).all() and (st4 == 0).all()
+    assert (s5 == s4).all()
+    dup = test_for_duplicate_haplotypes_with_alignment(ctx, [(y, x) for x, y in cases])
+    assert dup == [int(s) / len(x) >= 0.97 for s, (x, _y) in zip(s4, cases)]
+    assert any(dup) and not all(dup)
