@@ -249,8 +249,14 @@ def main():
         return ctx.download(out=(scores_pin.numpy(), status_pin.numpy()))
 
     # ---- warm-up (also allocates device workspace) ----
-    for _ in range(max(3, args.warmup)):
+    # At least W (>= 3) steps AND at least ~2.5 s: the first GPU process on a fresh box runs its first few hundred
+    # milliseconds measurably slower (140 vs 102 ms per config2 step was seen with a 0.4 s warm-up), and the driver's
+    # bench is exactly that process.  The count actually done is what the JSON line reports as "warmup".
+    n_warm = 0
+    t_warm = time.perf_counter()
+    while n_warm < max(3, args.warmup) or (time.perf_counter() - t_warm < 2.5 and n_warm < 64):
         scores, status, ops, ops_off = e2e_step()
+        n_warm += 1
     assert (status == 0).all(), f"pair status != 0: {np.unique(status)}"
     n_ops_words = 0 if ops is None else len(ops)
     st0 = ctx.stats()
@@ -312,7 +318,7 @@ def main():
         int_ops = ops_per_cell * cells
         out = {
             "metric": "alignments_per_s", "value": value, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": cfg["desc"], "name": args.workload, "reads_per_gpu": args.reads, "pairs_per_gpu": n_pairs,
                        "preset": cfg["preset"], "want_cigar": want_cigar, "l2": "256 MiB flush between timed steps",
