@@ -218,7 +218,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        # rank 0 prints exactly one JSON line on stdout: NCCL's version banner / debug output (printed to stdout
+        # whenever NCCL_DEBUG is VERSION or higher, WARN included) goes to a file instead
+        os.environ["NCCL_DEBUG_FILE"] = "/tmp/sfc_bench_nccl.%h.%p.log"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

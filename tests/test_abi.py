@@ -77,3 +77,47 @@ def test_process_wfa2_cigar_string_mirror():
     al = process_wfa2_cigar_string(b"DDDDMMMXXMMMMIIIMMMM"[::-1])
     assert al is not None and al.ref_offset == 0 and cigar_to_string(al.cigar) == "4S3=2X4=3D4="
     assert process_wfa2_cigar_string(b"DDII") is None
+
+
+def test_rust_crate_binds_only_declared_symbols_with_matching_arity():
+    """rust/sawfish-cuda (source only: no Rust toolchain here) must bind symbols the header declares, with the same
+    number of parameters, and its #[repr(C)] structs must list the header's fields in the header's order."""
+    hdr = open(os.path.join(ROOT, "include", "sawfish_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    rs = open(os.path.join(ROOT, "rust", "sawfish-cuda", "src", "lib.rs")).read()
+    rs = re.sub(r"//[^\n]*", "", rs)
+
+    def arity(text, name, opener):
+        m = re.search(r"\b" + name + r"\s*\(", text)
+        assert m, name
+        depth, i = 1, m.end()
+        start = i
+        while depth:
+            depth += {"(": 1, ")": -1}.get(text[i], 0)
+            i += 1
+        args = text[start:i - 1].strip()
+        return 0 if args in ("", "void") else args.count(",") + 1
+
+    block = rs[rs.index('extern "C" {'):]
+    block = block[:block.index("\n}")]
+    bound = re.findall(r"pub fn (sfc_[a-z0-9_]+)", block)
+    assert len(bound) >= 15
+    for name in bound:
+        assert arity(block, name, "(") == arity(hdr, name, "("), name
+
+    def c_fields(struct):
+        body = dict((n, b) for b, n in re.findall(r"typedef struct \{([^{}]*)\}\s*([a-z0-9_]+);", hdr))[struct]
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                names += [n.strip().rstrip("_") for n in re.sub(r"^[a-z0-9_]+\s+", "", decl).split(",")]
+        return names
+
+    def rs_fields(struct):
+        body = re.search(r"pub struct " + struct + r"\s*\{(.*?)\}", rs, flags=re.S).group(1)
+        return [n.rstrip("_") for n in re.findall(r"pub ([a-z0-9_]+):", body)]
+
+    assert rs_fields("SfcPenalties") == c_fields("sfc_penalties")
+    assert rs_fields("SfcPair") == c_fields("sfc_pair")
+    assert rs_fields("SfcBioScoring") == c_fields("sfc_bio_scoring")
