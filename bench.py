@@ -36,10 +36,13 @@ WORKLOADS = {
                      desc="score_sv-shaped: 100-500 bp read flank x ref/alt allele flanks, gap-linear, score only"),
     "config3": dict(preset="large_indel", want_cigar=True,
                     desc="refine_sv-shaped: contig vs reference window (+2-region N spacer), gap-affine-2p + CIGAR"),
+    "config4": dict(preset="consensus", want_cigar=False,
+                    desc="configs[3] in miniature: 8-sample joint-call, per SV group x sample x read x breakend x registration x allele "
+                         "flank pairs (100-500 bp, truncations, overlapping haplotypes), gap-linear, score only; --reads = SV groups per GPU"),
     "config5": dict(preset="large_indel", want_cigar=True,
                     desc="stress: 10-50 kb insertion/duplication haplotypes at 1-5% divergence"),
 }
-DEFAULT_READS = {"config2": 1024, "config2_linear": 1024, "config2b": 200000, "config3": 512, "config5": 8}
+DEFAULT_READS = {"config4": 96, "config2": 1024, "config2_linear": 1024, "config2b": 200000, "config3": 512, "config5": 8}
 
 
 def make_batch(workload, n_reads, seed):
@@ -50,6 +53,10 @@ def make_batch(workload, n_reads, seed):
         arena, pairs, _ = synth.config2b_score_sv_flanks(n_reads, seed=seed)
     elif workload == "config3":
         arena, pairs = synth.config3_refine_contigs(n_reads, seed=seed)
+    elif workload == "config4":
+        from sawfish_b200 import score_sv
+        builder, _meta = score_sv.synth_sv_groups(n_reads, n_samples=8, depth=30, seed=seed)
+        arena, pairs = builder.finish()
     else:
         arena, pairs = synth.config5_stress(n_reads, seed=seed)
     return arena, pairs
