@@ -1048,9 +1048,30 @@ extern "C" int sfc_multi_align_batch(sfc_multi* m, const sfc_penalties* pen, con
   const int nd = (int)m->ctx.size();
   // ---- plan: LPT over groups by estimated work.  Without caller groups, runs of consecutive pairs form the groups
   // (consecutive pairs share reads / loci in the callers), which keeps the plan O(n) instead of a sort over every pair.
+  // (the per-pair estimate and the bounds check are split over a few host threads: at 10^5-10^6 pairs per batch the
+  // serial part of this call is what limits strong scaling over 8 GPUs)
   std::vector<uint64_t> work(n);
-  int rc = sfc_estimate_pair_work(pen, pairs, n, work.data());
-  if (rc) { m->err = "invalid penalties"; return rc; }
+  int rc = 0;
+  {
+    AdjPen a_chk;
+    if (adjust_penalties(pen, &a_chk)) { m->err = "invalid penalties"; return SFC_ERR_INVALID; }
+    const size_t T = std::max<size_t>(1, std::min<size_t>(16, n / 32768));
+    std::vector<int> trc(T, 0);
+    std::vector<std::thread> pt;
+    for (size_t t = 0; t < T; ++t) {
+      pt.emplace_back([&, t]() {
+        const size_t b = n * t / T, e = n * (t + 1) / T;
+        trc[t] = sfc_estimate_pair_work(pen, pairs + b, e - b, work.data() + b);
+        for (size_t i = b; i < e && !trc[t]; ++i)
+          if (pairs[i].pattern_off + pairs[i].pattern_len > arena_len || pairs[i].text_off + pairs[i].text_len > arena_len) trc[t] = -100;
+      });
+    }
+    for (auto& t : pt) t.join();
+    for (int v : trc) {
+      if (v == -100) { m->err = "sequence outside arena"; return SFC_ERR_INVALID; }
+      if (v) { m->err = "invalid penalties"; return v; }
+    }
+  }
   const size_t run = group_of_pair ? 1 : std::max<size_t>(1, std::min<size_t>(256, n / ((size_t)nd * 64) + 1));
   auto group_of = [&](size_t i) -> uint32_t { return group_of_pair ? group_of_pair[i] : (uint32_t)(i / run); };
   uint32_t n_groups = 0;
@@ -1068,30 +1089,9 @@ extern "C" int sfc_multi_align_batch(sfc_multi* m, const sfc_penalties* pen, con
     int rc = 0;
   };
   std::vector<Shard> sh((size_t)nd);
-  for (size_t i = 0; i < n; ++i) {
-    const sfc_pair& p = pairs[i];
-    if (p.pattern_off + p.pattern_len > arena_len || p.text_off + p.text_len > arena_len) { m->err = "sequence outside arena"; return SFC_ERR_INVALID; }
-    sh[shard_of_group[group_of(i)]].idx.push_back((uint32_t)i);
-  }
-  for (int d = 0; d < nd; ++d) {
-    Shard& s = sh[(size_t)d];
-    sfc_multi::Stage& st = m->stage[(size_t)d];
-    uint64_t last_t_off = ~0ull;
-    uint32_t last_t_len = 0;
-    size_t bytes = 0;
-    for (uint32_t i : s.idx) {  // pass 1: size (consecutive pairs usually share their text: one read flank, several alleles)
-      const sfc_pair& q = pairs[i];
-      if (!(q.text_off == last_t_off && q.text_len == last_t_len)) { bytes += q.text_len; last_t_off = q.text_off; last_t_len = q.text_len; }
-      bytes += q.pattern_len;
-    }
-    if (pinned_reserve(st.arena, st.arena_cap, bytes) || pinned_reserve(st.pairs, st.pairs_cap, s.idx.size()) ||
-        pinned_reserve(st.scores, st.scores_cap, s.idx.size()) || pinned_reserve(st.status, st.status_cap, s.idx.size())) {
-      m->err = "pinned staging allocation failed";
-      return SFC_ERR_OOM;
-    }
-    s.arena_bytes = bytes;
-  }
-  // ---- one submitter thread per GPU: compaction (pass 2), upload, kernels, download ----
+  for (int d = 0; d < nd; ++d) sh[(size_t)d].idx.reserve(n / (size_t)nd + n / 8 + 16);
+  for (size_t i = 0; i < n; ++i) sh[shard_of_group[group_of(i)]].idx.push_back((uint32_t)i);
+  // ---- one submitter thread per GPU: sizing (pass 1), compaction (pass 2), upload, kernels, download ----
   std::vector<std::thread> th;
   for (int d = 0; d < nd; ++d) {
     th.emplace_back([&, d]() {
@@ -1099,6 +1099,23 @@ extern "C" int sfc_multi_align_batch(sfc_multi* m, const sfc_penalties* pen, con
       sfc_multi::Stage& st = m->stage[(size_t)d];
       m->kernel_ms[(size_t)d] = 0.0;
       if (s.idx.empty()) return;
+      {
+        uint64_t lt_off = ~0ull;
+        uint32_t lt_len = 0;
+        size_t bytes = 0;
+        for (uint32_t i : s.idx) {  // pass 1: size (consecutive pairs usually share their text: one read flank, several alleles)
+          const sfc_pair& q = pairs[i];
+          if (!(q.text_off == lt_off && q.text_len == lt_len)) { bytes += q.text_len; lt_off = q.text_off; lt_len = q.text_len; }
+          bytes += q.pattern_len;
+        }
+        cudaSetDevice(m->ctx[(size_t)d]->device);
+        if (pinned_reserve(st.arena, st.arena_cap, bytes) || pinned_reserve(st.pairs, st.pairs_cap, s.idx.size()) ||
+            pinned_reserve(st.scores, st.scores_cap, s.idx.size()) || pinned_reserve(st.status, st.status_cap, s.idx.size())) {
+          s.rc = SFC_ERR_OOM;
+          return;
+        }
+        s.arena_bytes = bytes;
+      }
       uint64_t last_t_off = ~0ull, last_t_new = 0, pos = 0;
       uint32_t last_t_len = 0;
       for (size_t j = 0; j < s.idx.size(); ++j) {
@@ -1134,6 +1151,7 @@ extern "C" int sfc_multi_align_batch(sfc_multi* m, const sfc_penalties* pen, con
   }
   for (auto& t : th) t.join();
   for (int d = 0; d < nd; ++d) {
+    if (sh[(size_t)d].rc == SFC_ERR_OOM && sh[(size_t)d].arena_bytes == 0) { m->err = "pinned staging allocation failed"; return SFC_ERR_OOM; }
     if (sh[(size_t)d].rc) { m->err = std::string("device ") + std::to_string(d) + ": " + sfc_last_error(m->ctx[(size_t)d]); return sh[(size_t)d].rc; }
   }
   if (want_cigar) {
