@@ -2,7 +2,7 @@
 """K4 (rust-bio style merge aligner) on merge-shaped pairs: base contig 0.6-10 kb x query high-quality range of a
 near-identical contig (reference src/joint_call/merge_haplotypes/single_region/merge_pools.rs:214-272).
 Prints one JSON line: GPU alignments/s and GCUPS (cells = |x| * |y|), CPU oracle (one thread) on a bounded sample, parity
-of scores on that sample.  usage: python tools/bench_merge.py [n_pairs] [cpu_seconds]"""
+of scores on that sample.  usage: python tests/tools/bench_merge.py [n_pairs] [cpu_seconds]"""
 import json
 import os
 import sys
@@ -10,7 +10,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import oracle as O  # noqa: E402  (CPU baseline leg only)
 from sawfish_b200.batch import AlignContext, PAIR_DTYPE  # noqa: E402

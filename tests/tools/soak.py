@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Soak test: many seeded batches of every shape through the CUDA path vs the oracle (run on the GPU box).
-usage: python tools/soak.py [seconds]"""
+usage: python tests/tools/soak.py [seconds]"""
 import os
 import sys
 import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import compare_with_oracle  # noqa: E402
