@@ -1,0 +1,186 @@
+"""contig.alignment.bam, the discover -> joint-call hand-off for assembled contigs (src/contig_output.rs:103-268 written,
+src/joint_call/get_refined_svs.rs:38-195 read): round trip, BGZF/BAM structure, htslib-written files, and the hand-off
+feeding the merge aligner's caller."""
+import gzip
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from sawfish_b200 import contig_bam as CB
+from sawfish_b200 import merge_pools as MP
+
+CHROMS = [("chr1", 248956422), ("chr20", 64444167)]
+
+
+def _contigs(rng, n_clusters=5):
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    out = []
+    for ci in range(n_clusters):
+        for ai in range(int(rng.integers(1, 3))):
+            L = int(rng.integers(301, 900))  # odd and even lengths: 4-bit packing
+            seq = acgt[rng.integers(0, 4, L)].tobytes()
+            hq = (int(rng.integers(0, 50)), L - int(rng.integers(0, 50)))
+            nreads = int(rng.integers(2, 40))
+            pos = int(rng.integers(1000, 60_000_000))
+            if ci % 2 == 0:   # indel-like: one segment
+                a = L // 2
+                segs = [CB.ContigAlignmentSegment(1, pos, [("=", a), ("I", 37), ("=", L - a - 37)])]
+            else:             # breakpoint: two segments, the second on the reverse strand for every other cluster
+                a = L // 2
+                segs = [CB.ContigAlignmentSegment(1, pos, [("=", a), ("S", L - a)]),
+                        CB.ContigAlignmentSegment(0, pos + 5000, [("S", a), ("=", L - a)], is_fwd_strand=(ci % 4 == 1))]
+            for sid in range(len(segs)):
+                out.append(CB.ContigAlignmentInfo(0, ci, ai, seq, sid, segs, nreads, hq))
+    return out
+
+
+def test_round_trip_and_joint_call_view(tmp_path):
+    rng = np.random.default_rng(7)
+    contigs = _contigs(rng)
+    path = str(tmp_path / CB.CONTIG_ALIGNMENT_FILENAME)
+    CB.write_contig_alignments(path, CHROMS, contigs, cmdline="sawfish discover --bam x.bam")
+    chroms, recs = CB.read_bam(path)
+    assert chroms == CHROMS and len(recs) == len(contigs)
+    keys = [(r.tid, r.pos) for r in recs]
+    assert keys == sorted(keys)                                            # coordinate-sorted (:228-233)
+    by_name = {}
+    for r in recs:
+        by_name.setdefault(r.qname, []).append(r)
+    for ca in contigs:
+        r = [x for x in by_name[f"sawfish:0:{ca.cluster_index}:{ca.assembly_index}"]
+             if bool(x.flag & CB.BAM_FSUPPLEMENTARY) == (ca.segment_id != 0)][0]
+        seg = ca.get_segment()
+        assert (r.tid, r.pos, r.mapq, r.cigar, r.seq) == (seg.tid, seg.pos, 20, seg.cigar, ca.seq)
+        assert bool(r.flag & CB.BAM_FREVERSE) == (not seg.is_fwd_strand)
+        assert CB.get_supporting_read_count(r) == ca.supporting_read_count
+        assert CB.get_high_quality_contig_range(r) == ca.high_quality_contig_range
+        assert (CB.SA_AUX_TAG in r.aux) == (len(ca.segments) > 1)
+    # joint-call's view: primary records only, breakend 2 rebuilt from the SA tag
+    assemblies = CB.get_candidate_sv_contig_info(path)
+    for ca in contigs:
+        if ca.segment_id != 0:
+            continue
+        got = assemblies[ca.cluster_index][ca.assembly_index]
+        assert got.supporting_read_count == ca.supporting_read_count
+        assert len(got.contig_alignments) == len(ca.segments)
+        p = got.contig_alignments[0]
+        assert (p.contig_seq, p.chrom_index, p.contig_alignment.ref_offset, p.contig_alignment.cigar, p.is_fwd_strand) == \
+               (ca.seq, ca.segments[0].tid, ca.segments[0].pos, ca.segments[0].cigar, True)
+        assert p.high_quality_contig_range == ca.high_quality_contig_range
+        if len(ca.segments) > 1:
+            s, seg = got.contig_alignments[1], ca.segments[1]
+            assert (s.chrom_index, s.contig_alignment.ref_offset, s.contig_alignment.cigar, s.is_fwd_strand) == \
+                   (seg.tid, seg.pos, seg.cigar, seg.is_fwd_strand)
+            if seg.is_fwd_strand:
+                assert s.contig_seq == ca.seq and s.high_quality_contig_range == ca.high_quality_contig_range
+            else:
+                lo, hi = ca.high_quality_contig_range
+                assert s.contig_seq == CB.rev_comp(ca.seq)
+                assert s.high_quality_contig_range == (len(ca.seq) - hi, len(ca.seq) - lo)
+
+
+def test_bgzf_structure(tmp_path):
+    rng = np.random.default_rng(8)
+    path = str(tmp_path / "c.bam")
+    CB.write_contig_alignments(path, CHROMS, _contigs(rng, n_clusters=120))    # several BGZF blocks
+    raw = open(path, "rb").read()
+    assert raw.endswith(CB._BGZF_EOF)
+    o, blocks, total = 0, 0, 0
+    while o < len(raw):
+        assert raw[o:o + 4] == b"\x1f\x8b\x08\x04" and raw[o + 12:o + 16] == b"BC\x02\x00"
+        (bsize,) = struct.unpack_from("<H", raw, o + 16)
+        (isize,) = struct.unpack_from("<I", raw, o + bsize + 1 - 4)
+        assert isize <= 65536
+        total += isize
+        o += bsize + 1
+        blocks += 1
+    assert o == len(raw) and blocks > 3
+    assert len(gzip.open(path, "rb").read()) == total
+    assert CB.reg2bin(0, 1) == 4681 and CB.reg2bin(1 << 14, (1 << 14) + 1) == 4682 and CB.reg2bin(0, 1 << 29) == 0
+
+
+def test_reads_htslib_written_bams():
+    """The reference's own test BAMs (written by htslib) parse with the same reader.  They live under /root/reference,
+    which exists only in the build container: skipped elsewhere."""
+    d = "/root/reference/test_data"
+    if not os.path.exists(os.path.join(d, "header_only.bam")):
+        pytest.skip("reference test data not present")
+    chroms, recs = CB.read_bam(os.path.join(d, "header_only.bam"))
+    assert len(chroms) > 0 and recs == []
+    assert all(isinstance(n, str) and ln > 0 for n, ln in chroms)
+    chroms2, recs2 = CB.read_bam(os.path.join(d, "minimal.bam"))
+    assert recs2 == []
+
+
+def _discover_dirs(rng, tmp_path, n_samples):
+    """One locus, a few true alleles, every sample writes its assembled contigs to its own discover dir."""
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    left, right = acgt[rng.integers(0, 4, 250)], acgt[rng.integers(0, 4, 250)]
+    alleles = [np.concatenate([left, acgt[rng.integers(0, 4, int(rng.integers(40, 140)))], right]) for _ in range(3)]
+    dirs, truth = [], []
+    for s in range(n_samples):
+        picks = rng.choice(3, size=int(rng.integers(1, 3)), replace=False)
+        contigs = []
+        for ai, a in enumerate(picks):
+            seq = alleles[int(a)].copy()
+            for _e in range(int(rng.integers(0, 3))):
+                seq[int(rng.integers(0, len(seq)))] = acgt[int(rng.integers(0, 4))]
+            ins = len(seq) - 500
+            segs = [CB.ContigAlignmentSegment(1, 40_000 + int(rng.choice([0, 2, 40])), [("=", 250), ("I", ins), ("=", 250)])]
+            contigs.append(CB.ContigAlignmentInfo(s, 0, ai, seq.tobytes(), 0, segs, int(rng.integers(3, 30)),
+                                                  (int(rng.integers(0, 20)), len(seq) - int(rng.integers(0, 20)))))
+            truth.append(int(a))
+        d = tmp_path / f"sample{s}"
+        d.mkdir()
+        CB.write_contig_alignments(str(d / CB.CONTIG_ALIGNMENT_FILENAME), CHROMS, contigs)
+        dirs.append(str(d))
+    return dirs, truth
+
+
+def _haplotypes_from_dirs(dirs):
+    haps, sample_lists = [], []
+    for d in dirs:
+        lst = []
+        for cluster in CB.get_candidate_sv_contig_info(os.path.join(d, CB.CONTIG_ALIGNMENT_FILENAME)):
+            for asm in cluster:
+                if not asm.contig_alignments:
+                    continue
+                a = asm.contig_alignments[0]
+                ins = [n for op, n in a.contig_alignment.cigar if op == "I"]
+                pos = a.contig_alignment.ref_offset + a.contig_alignment.cigar[0][1]
+                bp = MP.Breakpoint(MP.Breakend(a.chrom_index, pos), MP.Breakend(a.chrom_index, pos), ins[0] if ins else 0, 0)
+                lst.append(len(haps))
+                haps.append(MP.MergeHaplotype(a.contig_seq, a.high_quality_contig_range, asm.supporting_read_count, [bp]))
+        sample_lists.append(lst)
+    return haps, sample_lists
+
+
+def test_hand_off_feeds_the_merge_pools(tmp_path):
+    rng = np.random.default_rng(9)
+    dirs, truth = _discover_dirs(rng, tmp_path, n_samples=5)
+    haps, sample_lists = _haplotypes_from_dirs(dirs)
+    assert len(haps) == len(truth)
+    merge = O.bio_scoring(0, -2, 1, -3, yclip_prefix=0, yclip_suffix=0)
+    pools, _ = MP.get_haplotype_merge_pools(haps, sample_lists, lambda pairs: [O.bio_custom_align(merge, q, b)[0] for b, q in pairs])
+    for p in pools:
+        assert len({truth[h] for h in p}) <= 1        # only copies of the same allele were merged
+    assert sum(1 for p in pools if p) == len(set(truth))
+
+
+@pytest.mark.gpu
+def test_hand_off_feeds_the_merge_pools_gpu(tmp_path):
+    from sawfish_b200.batch import AlignContext
+    ctx = AlignContext(0)
+    rng = np.random.default_rng(10)
+    dirs, truth = _discover_dirs(rng, tmp_path, n_samples=8)
+    haps, sample_lists = _haplotypes_from_dirs(dirs)
+    merge = O.bio_scoring(0, -2, 1, -3, yclip_prefix=0, yclip_suffix=0)
+    want = MP.get_haplotype_merge_pools_sequential(haps, sample_lists, lambda b, q: O.bio_custom_align(merge, q, b)[0])
+    got, _ = MP.get_haplotype_merge_pools(haps, sample_lists, MP.gpu_merge_score_fn(ctx))
+    assert got == want
+    for p in got:
+        assert len({truth[h] for h in p}) <= 1
+    ctx.close()
