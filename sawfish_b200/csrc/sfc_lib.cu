@@ -459,7 +459,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     const int nG1 = a.e1 + 1, nG2 = a.e2 + 1;
     const int nslots = a.metric == 1 ? nM + 2 * nG1 + 2 * nG2 : nM;
 
-    struct Job { std::vector<uint32_t> list; int threads; int C; };
+    struct Job { std::vector<uint32_t> list; int threads; int C; double max_est = 0; };
     auto kernel_of = [&](bool wide) -> const void* {
       if (a.metric == 1) return wide ? (const void*)k2_align<true, int32_t> : (const void*)k2_align<true, int16_t>;
       return wide ? (const void*)k2_align<false, int32_t> : (const void*)k2_align<false, int16_t>;
@@ -496,13 +496,17 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
         Job j; j.threads = K2_LB_T; j.C = 1 << ci;
         if (const char* e = getenv("SFC_K2_THREADS")) j.threads = std::max(64, std::min(K2_LB_T, atoi(e)));  // experiment knob
         for (auto& t : tmp[ci]) j.list.push_back(t.second);
+        j.max_est = tmp[ci].front().first;  // sorted heaviest first
         jobs.push_back(std::move(j));
       }
     }
 
     // size one job's launch: returns grid (in clusters), slab bytes, shared bytes, win_cap
     struct Plan { size_t n_cl, slab, smem, max_fixed; int win_cap, stages; bool wide; };
-    auto plan_job = [&](const std::vector<uint32_t>& list, int threads, int C, size_t budget, int divisor, Plan* pl) -> int {
+    // max_est: estimated wavefront cells of the heaviest pair of the list (0 = unknown).  One choice byte is kept per cell,
+    // so the slab's choice-byte budget follows it: a pair that runs out is re-run from scratch in an escalation pass, at
+    // the tail of the batch, which costs far more than the memory does (180 GB of HBM).
+    auto plan_job = [&](const std::vector<uint32_t>& list, int threads, int C, size_t budget, int divisor, Plan* pl, double max_est = 0) -> int {
       size_t max_fixed = 0, max_win = 0, max_W = 0;
       bool wide = false;
       for (uint32_t pi : list) wide = wide || c->h_pairs[pi].plen > K2_MAX_LEN16 || c->h_pairs[pi].tlen > K2_MAX_LEN16;
@@ -543,6 +547,8 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       if (const char* e = getenv("SFC_K2_SLOT_DIV")) slots = std::max<size_t>(1, slots / std::max(1, atoi(e)));  // experiment knob
       size_t n_cl = std::max<size_t>(1, std::min<size_t>(list.size(), slots) / divisor);
       size_t bt_want = std::min<size_t>(std::max<size_t>((size_t)2048 * max_W * divisor, (size_t)4 << 20), (size_t)8 << 30);
+      if (max_est > 0 && !getenv("SFC_K2_NO_EST_SLAB"))
+        bt_want = std::min<size_t>(std::max<size_t>(bt_want, (size_t)(1.5 * max_est) + ((size_t)1 << 20)), (size_t)8 << 30);
       size_t slab = max_fixed + bt_want;
       while (n_cl > 1 && slab * n_cl > budget) n_cl = (n_cl + 1) / 2;
       if (slab * n_cl > budget) slab = budget;
@@ -603,14 +609,14 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       size_t demand_total = 0;
       std::vector<size_t> demand(jobs.size());
       for (size_t j = 0; j < jobs.size(); ++j) {
-        if ((rc = plan_job(jobs[j].list, jobs[j].threads, jobs[j].C, avail, 1, &plans[j]))) return rc;
+        if ((rc = plan_job(jobs[j].list, jobs[j].threads, jobs[j].C, avail, 1, &plans[j], jobs[j].max_est))) return rc;
         demand[j] = plans[j].slab * plans[j].n_cl;
         demand_total += demand[j];
       }
       if (demand_total > avail) {
         for (size_t j = 0; j < jobs.size(); ++j) {
           const size_t budget = std::max<size_t>((size_t)((double)avail * ((double)demand[j] / (double)demand_total)), plans[j].max_fixed + (1 << 20));
-          if ((rc = plan_job(jobs[j].list, jobs[j].threads, jobs[j].C, budget, 1, &plans[j]))) return rc;
+          if ((rc = plan_job(jobs[j].list, jobs[j].threads, jobs[j].C, budget, 1, &plans[j], jobs[j].max_est))) return rc;
         }
       }
       size_t need = 0;

@@ -11,5 +11,5 @@ python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_config2_defaul
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_config2_default.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_launches_c2.log 2>&1
 python bench.py --workload config2b --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_config2b_default.json 2> $O/bench_config2b.err && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_config2b_default.csv python bench.py --workload config2b --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_launches_c2b.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k2_align -c 2 -f -o $O/ncu_k2_config2 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_k2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k2_align -c 4 -f -o $O/ncu_k2_config2 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_k2.log 2>&1
 ls -la $O
