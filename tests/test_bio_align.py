@@ -290,3 +290,70 @@ def test_k5_agrees_with_k4_on_merge_shaped_pairs():
     dup = test_for_duplicate_haplotypes_with_alignment(ctx, [(y, x) for x, y in cases])
     assert dup == [int(s) / len(x) >= 0.97 for s, (x, _y) in zip(s4, cases)]
     assert any(dup) and not all(dup)
+
+
+def _k5_reduced_score(sc, x: bytes, y: bytes) -> int:
+    """The recurrence K5 runs (sfc_k_bio_score.cuh), written out row by row: no y-prefix-clip candidate, no x-suffix clip,
+    no traceback, final passes folded into one maximum.  Must equal the full oracle whenever K5 accepts the scoring."""
+    go, ge, ma, mi = sc.gap_open, sc.gap_extend, sc.match, sc.mismatch
+    xp, yp, ys = sc.xclip_prefix, sc.yclip_prefix, sc.yclip_suffix
+    m, n, goe = len(x), len(y), sc.gap_open + sc.gap_extend
+    xp_on = xp > O.BIO_MIN_SCORE // 2 if hasattr(O, "BIO_MIN_SCORE") else xp > -858993459 // 2
+    s0 = [0] * (n + 1)
+    sn0 = ys
+    for j in range(1, n + 1):
+        d0 = goe if j == 1 else max(go + ge * j, yp + goe)
+        s0[j] = max(d0, yp)
+        if j < n:
+            sn0 = max(sn0, s0[j] + ys)
+    s0[n] = max(s0[n], sn0)
+    col0_i = lambda i: goe if i == 1 else max(go + ge * i, xp + goe)  # noqa: E731
+    s_prev, i_prev = s0, [-858993459] * (n + 1)
+    best = s0[n] + m * goe
+    for i in range(1, m + 1):
+        s_row, i_row = [0] * (n + 1), [0] * (n + 1)
+        s_row[0], i_row[0] = max(col0_i(i), xp), col0_i(i)
+        d, snmax = -858993459, s_row[0]
+        for j in range(1, n + 1):
+            ms = s_prev[j - 1] + (ma if x[i - 1] == y[j - 1] else mi)
+            iv = max(i_prev[j] + ge, s_prev[j] + goe)
+            d = max(d + ge, s_row[j - 1] + goe)
+            s = max(ms, iv, d)
+            if xp_on:
+                s = max(s, xp + max(yp, go + ge * j))
+            s_row[j], i_row[j] = s, iv
+            snmax = max(snmax, s)
+        best = max(best, max(s_row[n], snmax + ys) + (m - i) * goe)
+        s_prev, i_prev = s_row, i_row
+    return best
+
+
+def test_k5_reduced_recurrence_equals_the_oracle_on_cpu():
+    """The three simplifications K5 relies on (kernel header) hold for every scoring it accepts: x-suffix clip disabled,
+    clip penalties <= 0.  Checked here on the CPU so the argument is pinned independently of the GPU run."""
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    flavours = {
+        "merge": O.bio_scoring(0, -2, 1, -3, yclip_prefix=0, yclip_suffix=0),
+        "glocal": O.bio_scoring(-1, -1, 1, -3, yclip_prefix=0, yclip_suffix=0),
+        "prefix": O.bio_scoring(-1, -1, 1, -3, yclip_suffix=0, xclip_prefix=0),
+        "global": O.bio_scoring(-3, -1, 1, -2),
+        "clips_paid": O.bio_scoring(-2, -1, 1, -3, xclip_prefix=-4, yclip_prefix=-3, yclip_suffix=-5),
+        "ysuffix_only": O.bio_scoring(-2, -1, 1, -3, yclip_suffix=-1),
+        "xprefix_only": O.bio_scoring(-2, -1, 1, -3, xclip_prefix=-1),
+    }
+    for name, sc in flavours.items():
+        for _ in range(120):
+            n = int(rng.integers(1, 36))
+            y = acgt[rng.integers(0, 4, n)]
+            if rng.random() < 0.6 and n > 3:
+                a = int(rng.integers(0, n - 1))
+                x = y[a:int(rng.integers(a + 1, n + 1))].copy()
+                for _e in range(int(rng.integers(0, 3))):
+                    x[int(rng.integers(0, len(x)))] = acgt[int(rng.integers(0, 4))]
+                if rng.random() < 0.3:
+                    x = np.insert(x, int(rng.integers(0, len(x) + 1)), acgt[rng.integers(0, 4, int(rng.integers(1, 5)))])
+            else:
+                x = acgt[rng.integers(0, 4, int(rng.integers(1, 36)))]
+            xb, yb = x.tobytes(), y.tobytes()
+            assert _k5_reduced_score(sc, xb, yb) == O.bio_custom_align(sc, xb, yb)[0], (name, xb, yb)
