@@ -179,8 +179,10 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
           const int k = k0 + j;
           off[j] = cell[j] >> 16;
           if ((unsigned)off[j] > (unsigned)tlen || (unsigned)(off[j] - k) > (unsigned)plen) { cell[j] = WNULL; off[j] = -1; }
-          const bool valid = off[j] >= 0;
-          xw[j] = window8(wp, valid ? off[j] - k : 0) ^ window8(wt, valid ? off[j] : 0);
+          // no address guard for null cells (off = -1): pattern index -1 - k lies between -(tlen + 1) and plen - 1 and text
+          // index -1 just below 0, i.e. inside this group's own shared memory (the ring precedes the pattern windows, the
+          // pattern windows precede the text windows); what is loaded there is never used.
+          xw[j] = window8(wp, off[j] - k) ^ window8(wt, off[j]);
         }
         bool more = false, edge = false;
 #pragma unroll

@@ -357,3 +357,29 @@ def test_k5_reduced_recurrence_equals_the_oracle_on_cpu():
                 x = acgt[rng.integers(0, 4, int(rng.integers(1, 36)))]
             xb, yb = x.tobytes(), y.tobytes()
             assert _k5_reduced_score(sc, xb, yb) == O.bio_custom_align(sc, xb, yb)[0], (name, xb, yb)
+
+
+@pytest.mark.gpu
+def test_k5_rejects_what_the_reference_asserts_on():
+    """assert!(!text.is_empty()) / assert!(!pattern.is_empty()) (src/bio_align_utils.rs:177-178) become SFC_ERR_INVALID;
+    so do pairs outside the arena and positive gap penalties.  A scoring with an enabled x-suffix clip is still served
+    (by K4 behind the same entry point) with the oracle's score."""
+    from sawfish_b200 import SfcError
+    from sawfish_b200.batch import AlignContext, PAIR_DTYPE
+    ctx = AlignContext(0)
+    arena = np.frombuffer(b"ACGTACGTAC" + b"ACGTTCGTAC", np.uint8).copy()
+    ok = np.array([(0, 10, 10, 10, 0, 0, 0, 0, 0)], dtype=PAIR_DTYPE)
+    merge = _to_gpu_scoring(scorings()["merge"])
+    scores, status = ctx.bio_score_batch(merge, arena, ok)
+    assert status[0] == 0 and scores[0] == O.bio_custom_align(scorings()["merge"], b"ACGTACGTAC", b"ACGTTCGTAC")[0]
+    for bad in [(0, 10, 0, 10, 0, 0, 0, 0, 0), (0, 10, 10, 0, 0, 0, 0, 0, 0), (0, 15, 10, 10, 0, 0, 0, 0, 0)]:
+        with pytest.raises(SfcError) as ei:
+            ctx.bio_score_batch(merge, arena, np.array([bad], dtype=PAIR_DTYPE))
+        assert ei.value.code == -1
+    pos_gap = _to_gpu_scoring(O.bio_scoring(1, -1, 1, -3))
+    with pytest.raises(SfcError):
+        ctx.bio_score_batch(pos_gap, arena, ok)
+    suffix = scorings()["suffix"]  # x-suffix clip enabled: routed to K4
+    s2, st2 = ctx.bio_score_batch(_to_gpu_scoring(suffix), arena, ok)
+    assert st2[0] == 0 and s2[0] == O.bio_custom_align(suffix, b"ACGTACGTAC", b"ACGTTCGTAC")[0]
+    ctx.close()
