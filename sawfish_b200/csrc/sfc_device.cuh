@@ -33,7 +33,7 @@ struct SeqDesc {
 // win[i] = (word[i], word[i+1]) so that one 8-byte shared load + one funnel shift yields the window.
 __device__ __forceinline__ uint32_t window8(const uint2* __restrict__ win, int pos) {
   const uint2 u = win[pos >> 3];
-  return __funnelshift_r(u.x, u.y, (pos & 7) << 2);
+  return __funnelshift_r(u.x, u.y, pos << 2);  // the funnel shift uses its amount modulo 32: (pos << 2) & 31 == (pos & 7) << 2
 }
 
 // number of leading equal bases given xor of two windows (x != 0)

@@ -184,14 +184,16 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
           // pattern windows precede the text windows); what is loaded there is never used.
           xw[j] = window8(wp, off[j] - k) ^ window8(wt, off[j]);
         }
-        bool more = false, edge = false;
+        int advmax = 0;  // 8 <=> some live cell matched its whole first window (lead_eq is at most 7)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const bool valid = off[j] >= 0;
-          if (valid) off[j] += xw[j] ? lead_eq(xw[j]) : 8;
-          more = more || (valid && xw[j] == 0u);
+          const int adv = xw[j] ? lead_eq(xw[j]) : 8;  // straight-line: no branch per cell
+          const int a = off[j] >= 0 ? adv : 0;
+          off[j] += a;
+          cell[j] += a << 16;  // the offset field moves with it (null cells: a = 0)
+          advmax = max(advmax, a);
         }
-        if (__any_sync(FULL, more)) {  // rare: a run longer than 8 bases (the true diagonal)
+        if (__any_sync(FULL, advmax == 8)) {  // rare: a run longer than 8 bases (the true diagonal)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int k = k0 + j;
@@ -209,14 +211,13 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
               const int adv = coop_extend(wp, wt, plen, tlen, ko, ho, lane);
               if (lane == src) off[j] += adv;
             }
+            if (off[j] >= 0) cell[j] = (cell[j] & 0xFFFF) | (off[j] << 16);
           }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (off[j] >= 0) cell[j] = (cell[j] & 0xFFFF) | (off[j] << 16);
-          edge = edge || off[j] >= tlen || off[j] - (k0 + j) >= plen;
-        }
-        if (edge) {  // a cell touches the end of a sequence: full ends-free termination test (rare)
+        // a cell touches the end of a sequence <=> the largest text / pattern position of the four does
+        const int hmax = max(max(off[0], off[1]), max(off[2], off[3]));
+        const int vmax = max(max(off[0] - k0, off[1] - k0 - 1), max(off[2] - k0 - 2, off[3] - k0 - 3));
+        if (hmax >= tlen || vmax >= plen) {  // a cell touches the end of a sequence: full ends-free termination test (rare)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int k = k0 + j, v = off[j] - k;
