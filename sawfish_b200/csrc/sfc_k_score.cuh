@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
         int advmax = 0;  // 8 <=> some live cell matched its whole first window (lead_eq is at most 7)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int adv = xw[j] ? lead_eq(xw[j]) : 8;  // straight-line: no branch per cell
+          const int adv = (int)min(((unsigned)(__ffs((int)xw[j]) - 1)) >> 2, 8u);  // equal bases in the window; 8 when xw == 0 (ffs = 0)
           const int a = off[j] >= 0 ? adv : 0;
           off[j] += a;
           cell[j] += a << 16;  // the offset field moves with it (null cells: a = 0)
