@@ -22,8 +22,9 @@
 // band goes to a boundary array (8 bytes per column, L2 resident) that the warp doing the next band reads 32 columns
 // at a time, one batch ahead, as soon as a progress word in shared memory says they are there: the four warps work on
 // four consecutive bands at once, each 64 columns behind the previous one (band b reads buffer b % 5, writes buffer
-// (b + 1) % 5; the warp that last read a buffer is the one that overwrites it, so producers never wait).  ~8 integer instructions per matrix cell (ISETP, SEL, IADD, 2 x VIADDMNMX, VIMNMX3,
-// IADD, VIMNMX); bound by INT32 issue.  No tensor cores (integer DP).
+// (b + 1) % 5; the warp that last read a buffer is the one that overwrites it, so producers never wait).  10 integer instructions per matrix cell: 6 on the alu pipe
+// (4 x VIADDMNMX, 2 x VIMNMX), 4 on the fma pipe (the substitution score as dg + ma - min((x - y)^2, 1) * (ma - mi)); bound by
+// the alu pipe (ncu: 86.6 % busy in the 7-alu-instruction version).  No tensor cores (integer DP).
 #pragma once
 #include "sfc_k_bio.cuh"
 
@@ -72,7 +73,7 @@ __device__ __forceinline__ int k5_band(const K4Scoring& sc, const uint8_t* __res
                                        const int m, const int n, const int i0, const int2* in, int2* out,
                                        const volatile int* prog_in, volatile int* prog_out, const int tag,
                                        const int lane) {
-  const int ge = sc.ge, goe = sc.go + sc.ge;
+  const int ge = sc.ge, goe = sc.go + sc.ge, dsub = sc.ma - sc.mi;
   int xb[R], SpG[R], Dp[R], SnG[R];
   const int top = i0 + lane * R;  // the row above this lane's first row
   auto col0_I = [&](int i) { return i == 1 ? goe : max(sc.go + ge * i, sc.xp + goe); };
@@ -103,15 +104,19 @@ __device__ __forceinline__ int k5_band(const K4Scoring& sc, const uint8_t* __res
       // With G = go + ge added to every stored S:  T = max(diagonal, D) + G needs nothing from the row above, so the
       // only dependence that runs down the rows is  I(next row) = max(I + ge, T)  (I + G <= I + ge because go <= 0):
       // one VIADDMNMX per row on the critical path.
-      int dg = diag, I = upI, SG = upS;
+      int dgma = diag + sc.ma, I = upI, SG = upS;  // diagonal + match score; dsub = match - mismatch
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int msG = dg + (xb[r] == yc ? sc.ma : sc.mi);
+        // substitution score without compare + select (the alu pipe is the bound, 7 of 8 instructions per cell sat on it):
+        // (x - y)^2 is 0 for equal symbols and >= 1 otherwise; the subtract, the square and the final multiply-add issue on
+        // the fma pipe, only the min stays on the alu pipe
+        const int dxy = xb[r] - yc;
+        const int msG = dgma - min(dxy * dxy, 1) * dsub;
         const int D = max(Dp[r] + ge, SpG[r]);
         int T = max(D + goe, msG);
         if (XP) T = max(T, xclipjG);
         SG = max(I + goe, T);
-        dg = SpG[r];
+        dgma = SpG[r] + sc.ma;
         SpG[r] = SG; Dp[r] = D; SnG[r] = max(SnG[r], SG);
         I = max(I + ge, T);
       }
