@@ -270,17 +270,24 @@ extern "C" int sfc_batch_upload(sfc_ctx* c, const uint8_t* arena, size_t arena_l
   c->h_pairs.resize(n);
   c->h_seqs.resize(2 * n);
   c->h_seqwoff.resize(2 * n + 1);
+  int rc;
+  // the ASCII arena goes first: from pinned host memory its copy overlaps the host loop below (a few ms per 10^5 pairs)
+  if ((rc = ensure(c, c->d_arena, arena_len))) return rc;
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  CU(cudaMemcpyAsync(c->d_arena.p, arena, arena_len, cudaMemcpyHostToDevice, c->stream));
+  // an argument error below must not return while that copy still reads the caller's buffer
+  auto bad = [&](const char* fmt, size_t i) { cudaStreamSynchronize(c->stream); return fail(c, SFC_ERR_INVALID, fmt, i); };
   uint64_t woff = 0;
   for (size_t i = 0; i < n; ++i) {
     const sfc_pair& p = pairs[i];
-    if (p.pattern_len == 0 || p.text_len == 0) return fail(c, SFC_ERR_INVALID, "pair %zu: empty sequence", i);
-    if (p.pattern_len > 0x3FFFFFFFu || p.text_len > 0x3FFFFFFFu) return fail(c, SFC_ERR_INVALID, "pair %zu: sequence too long", i);
+    if (p.pattern_len == 0 || p.text_len == 0) return bad("pair %zu: empty sequence", i);
+    if (p.pattern_len > 0x3FFFFFFFu || p.text_len > 0x3FFFFFFFu) return bad("pair %zu: sequence too long", i);
     if (p.pattern_off + p.pattern_len > arena_len || p.text_off + p.text_len > arena_len)
-      return fail(c, SFC_ERR_INVALID, "pair %zu: sequence outside arena", i);
+      return bad("pair %zu: sequence outside arena", i);
     if (p.pattern_begin_free < 0 || p.pattern_end_free < 0 || p.text_begin_free < 0 || p.text_end_free < 0 ||
         (uint32_t)p.pattern_begin_free > p.pattern_len || (uint32_t)p.pattern_end_free > p.pattern_len ||
         (uint32_t)p.text_begin_free > p.text_len || (uint32_t)p.text_end_free > p.text_len)
-      return fail(c, SFC_ERR_INVALID, "pair %zu: ends-free allowance outside [0, len]", i);
+      return bad("pair %zu: ends-free allowance outside [0, len]", i);
     const uint32_t rev = (p.flags & SFC_PAIR_REVERSE) ? 1u : 0u;
     DevPair& d = c->h_pairs[i];
     d.plen = (int32_t)p.pattern_len; d.tlen = (int32_t)p.text_len;
@@ -291,18 +298,14 @@ extern "C" int sfc_batch_upload(sfc_ctx* c, const uint8_t* arena, size_t arena_l
     c->h_seqs[2 * i + 1] = SeqDesc{p.text_off, p.text_len, rev | 2u};
     c->h_seqwoff[2 * i + 1] = (uint32_t)woff; d.t_woff = (uint32_t)woff;
     woff += (p.text_len + 7) / 8 + 2;
-    if (woff > 0xFFFFFFF0ull) return fail(c, SFC_ERR_INVALID, "batch too large (packed arena exceeds 2^32 words)");
+    if (woff > 0xFFFFFFF0ull) return bad("batch too large (packed arena exceeds 2^32 words; pair %zu)", i);
   }
   c->h_seqwoff[2 * n] = (uint32_t)woff;
-  int rc;
-  if ((rc = ensure(c, c->d_arena, arena_len))) return rc;
-  if ((rc = ensure(c, c->d_nib, (size_t)woff * 4))) return rc;
-  if ((rc = ensure(c, c->d_seqs, 2 * n * sizeof(SeqDesc)))) return rc;
-  if ((rc = ensure(c, c->d_seqwoff, (2 * n + 1) * 4))) return rc;
-  if ((rc = ensure(c, c->d_pairs, n * sizeof(DevPair)))) return rc;
-  if ((rc = ensure(c, c->d_misc, 256))) return rc;
-  CU(cudaEventRecord(c->ev[0], c->stream));
-  CU(cudaMemcpyAsync(c->d_arena.p, arena, arena_len, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = ensure(c, c->d_nib, (size_t)woff * 4))) { cudaStreamSynchronize(c->stream); return rc; }
+  if ((rc = ensure(c, c->d_seqs, 2 * n * sizeof(SeqDesc)))) { cudaStreamSynchronize(c->stream); return rc; }
+  if ((rc = ensure(c, c->d_seqwoff, (2 * n + 1) * 4))) { cudaStreamSynchronize(c->stream); return rc; }
+  if ((rc = ensure(c, c->d_pairs, n * sizeof(DevPair)))) { cudaStreamSynchronize(c->stream); return rc; }
+  if ((rc = ensure(c, c->d_misc, 256))) { cudaStreamSynchronize(c->stream); return rc; }
   CU(cudaMemcpyAsync(c->d_seqs.p, c->h_seqs.data(), 2 * n * sizeof(SeqDesc), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_seqwoff.p, c->h_seqwoff.data(), (2 * n + 1) * 4, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_pairs.p, c->h_pairs.data(), n * sizeof(DevPair), cudaMemcpyHostToDevice, c->stream));
