@@ -184,3 +184,18 @@ def test_hand_off_feeds_the_merge_pools_gpu(tmp_path):
     for p in got:
         assert len({truth[h] for h in p}) <= 1
     ctx.close()
+
+
+def test_parse_bnd_alt_allele_reference_vectors():
+    """The reference's two unit tests (src/joint_call/get_refined_svs.rs:926-976), plus the mirrored orientations."""
+    from sawfish_b200.candidate_sv import LEFT_ANCHOR, RIGHT_ANCHOR, parse_bnd_alt_allele
+    for chrom in ("chr1", "HLA-DRB1*10:01:01"):
+        info = parse_bnd_alt_allele({chrom: 0}, f"TCT]{chrom}:500]".encode(), 10)
+        assert (info.breakend1_direction, info.breakend2_direction) == (LEFT_ANCHOR, LEFT_ANCHOR)
+        assert (info.breakend2_chrom_index, info.breakend2_pos, info.insert_seq) == (0, 489, b"CT")
+    info = parse_bnd_alt_allele({"chr1": 0}, b"T[chr1:500[", 10)      # left anchor joined to a right-anchored mate
+    assert (info.breakend1_direction, info.breakend2_direction, info.breakend2_pos, info.insert_seq) == (LEFT_ANCHOR, RIGHT_ANCHOR, 498, b"")
+    info = parse_bnd_alt_allele({"chr1": 0}, b"[chr1:500[GAT", 10)    # both right-anchored: homlen shift and the -1
+    assert (info.breakend1_direction, info.breakend2_direction, info.breakend2_pos, info.insert_seq) == (RIGHT_ANCHOR, RIGHT_ANCHOR, 488, b"GA")
+    with pytest.raises(ValueError):
+        parse_bnd_alt_allele({"chr1": 0}, b"TCT", 0)
