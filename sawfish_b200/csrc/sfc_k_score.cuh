@@ -151,20 +151,22 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
             bl = rowI[e0 - 1];
             br = rowI[e0 + 4];
           }
-          int32_t av[4] = {a.x, a.y, a.z, a.w};
-          int32_t bm[4] = {bl, b.x, b.y, b.z};  // k-1
-          int32_t bp[4] = {b.y, b.z, b.w, br};  // k+1
           const int kA = (gb << 2) - kbase;
-          if (!(kA >= ilo && kA + 127 <= ihi)) {  // boundary chunk: check each read against its source range
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int k = k0 + j;
-              const bool act = k >= lo && k <= hi;
-              av[j] = (act && (unsigned)(k - lox) < (unsigned)cntx) ? av[j] : WNULL;
-              bm[j] = (act && (unsigned)(k - 1 - loi) < (unsigned)cnti) ? bm[j] : WNULL;
-              bp[j] = (act && (unsigned)(k + 1 - loi) < (unsigned)cnti) ? bp[j] : WNULL;
-            }
+          if (!(kA >= ilo && kA + 127 <= ihi)) {
+            // boundary chunk: every element read is checked against its source row's live range — the four of the
+            // mismatch row and the SIX distinct ones of the indel row (k0-1 .. k0+4; the k-1 and k+1 neighbours of the
+            // four cells overlap).  No test against this wavefront's own [lo, hi]: a diagonal with a live source lies
+            // inside the union of the source ranges by construction, and diagonals outside the matrix are nulled by the
+            // bounds test below.
+            const unsigned dx = (unsigned)(k0 - lox), di = (unsigned)(k0 - 1 - loi), ux = (unsigned)cntx, ui = (unsigned)cnti;
+            a.x = dx < ux ? a.x : WNULL; a.y = dx + 1u < ux ? a.y : WNULL; a.z = dx + 2u < ux ? a.z : WNULL; a.w = dx + 3u < ux ? a.w : WNULL;
+            bl = di < ui ? bl : WNULL;
+            b.x = di + 1u < ui ? b.x : WNULL; b.y = di + 2u < ui ? b.y : WNULL; b.z = di + 3u < ui ? b.z : WNULL; b.w = di + 4u < ui ? b.w : WNULL;
+            br = di + 5u < ui ? br : WNULL;
           }
+          const int32_t av[4] = {a.x, a.y, a.z, a.w};
+          const int32_t bm[4] = {bl, b.x, b.y, b.z};  // k-1
+          const int32_t bp[4] = {b.y, b.z, b.w, br};  // k+1
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int32_t mis = av[j] + (K1_ONE | K1_TX), ins = bm[j] + K1_ONE, del = bp[j] | K1_TD;
