@@ -143,7 +143,13 @@ def cpu_reference_run(workload, arena, pairs, budget_s, threads=0):
     from oracle import oracle as O
     cfg = WORKLOADS[workload]
     pen = O.CONSENSUS if cfg["preset"] == "consensus" else O.LARGE_INDEL
-    threads = threads or O.max_threads()
+    if not threads:
+        # all host cores this process may run on.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to every
+        # rank, which would turn the N>1 reference arm into a one-thread baseline.
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or O.max_threads()
     opairs = pairs.astype(O.PAIR_DTYPE)
     n = len(opairs)
     done, secs, cells = 0, 0.0, 0
@@ -190,10 +196,30 @@ def run_reference(args, rank, world):
            "cpu_baseline": {"value": val, "unit": "alignments/s", "cores": info["cores"], "kind": "port", "sample": sample,
                             "note": "WFA2-semantics CPU restatement (oracle/), not the sawfish binary: no Rust toolchain / WFA2-lib here"},
            "e2e": {"value": val, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Rank 0 must print exactly ONE JSON line on stdout.  NCCL prints its version banner there (whenever NCCL_DEBUG is
+    VERSION or higher) and other libraries may chat too, so file descriptor 1 is pointed at stderr for the whole run and
+    the JSON line goes to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -228,6 +254,8 @@ def main():
         # rank 0 prints exactly one JSON line on stdout: NCCL's version banner / debug output (printed to stdout
         # whenever NCCL_DEBUG is VERSION or higher, WARN included) goes to a file instead
         os.environ["NCCL_DEBUG_FILE"] = "/tmp/sfc_bench_nccl.%h.%p.log"
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"  # the banner is printed at VERSION and WARN; INFO / TRACE are left to the user
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -357,7 +385,7 @@ def main():
                                    "sample": f"first {cb['pairs']} of {n_pairs} pairs of the step batch, {cb['seconds']:.1f} s",
                                    "gcups": cb["gcups"],
                                    "note": "WFA2-semantics CPU restatement (oracle/, OpenMP over pairs, fresh aligner state per pair)"}
-        print(json.dumps(out))
+        emit(out)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
