@@ -1,8 +1,10 @@
 """Pieces of the `candidate.sv.bcf` side of the discover -> joint-call hand-off that do not need a BCF parser.
 
-Reference: src/joint_call/get_refined_svs.rs.  Built so far: `parse_bnd_alt_allele` (:206-287), pinned by the reference's
-two unit tests (:926-976).  The BCF2 record reader itself (typed INFO values, string / contig dictionaries, :334-606) is
-not built; `sawfish_b200/contig_bam.py` covers the contig half of the hand-off.
+Reference: src/joint_call/get_refined_svs.rs.  Built: `parse_bnd_alt_allele` (:206-287), pinned by the reference's two unit
+tests (:926-976); `get_sv_id_from_label` (src/sv_id.rs:52-76); `process_record_to_anno_refined_sv`, the record -> breakpoint
+logic of `process_bcf_record_to_anno_refine_sv` (:334-552), fed from VCF text lines.  Not built: the BCF2 binary decoding
+(typed INFO values, string / contig dictionaries) the reference gets from htslib.  `sawfish_b200/contig_bam.py` covers the
+contig half of the hand-off.
 """
 from __future__ import annotations
 
@@ -50,3 +52,132 @@ def parse_bnd_alt_allele(label_to_index: Dict[str, int], alt_allele: bytes, homl
     if breakend2_direction == RIGHT_ANCHOR:
         pos -= 1
     return BndAltInfo(breakend1_direction, breakend2_chrom_index, pos, breakend2_direction, insert_seq)
+
+
+# ---------------------------------------------------------------------------------------------- records -> refined SVs
+# process_bcf_record_to_anno_refine_sv (:334-552) on a parsed record.  The reference reads `candidate.sv.bcf` through
+# htslib; the record CONTENT is what this mirrors (the same CHROM / POS / ID / ALT / INFO a `bcftools view` of that file
+# shows), fed here from VCF text lines.
+from typing import List, Optional, Tuple, Union  # noqa: E402
+
+CONTIG_POS_INFO_KEY, OVERLAP_ASM_INFO_KEY = "CONTIG_POS", "OVERLAP_ASM"        # src/large_variant_output.rs:23-24
+BND0_NEIGHBOR_INFO_KEY, BND1_NEIGHBOR_INFO_KEY = "BND0_NEIGHBOR", "BND1_NEIGHBOR"  # :25-26
+
+
+@dataclass(frozen=True)
+class SVUniqueIdData:  # src/sv_id.rs
+    sample_index: int
+    cluster_index: int
+    assembly_index: int
+    alignment_index: int
+
+
+def get_sv_id_from_label(label: str) -> Tuple[SVUniqueIdData, Optional[bool]]:
+    """src/sv_id.rs:52-76: "pkg:sample:cluster:assembly:alignment[:breakend]" -> (id, is_breakend1)."""
+    parts = label.split(":")
+    assert 5 <= len(parts) <= 6
+    sv_id = SVUniqueIdData(int(parts[1]), int(parts[2]), int(parts[3]), int(parts[4]))
+    return sv_id, (int(parts[5]) == 0 if len(parts) > 5 else None)
+
+
+@dataclass
+class CandidateRecord:
+    chrom_index: int
+    pos: int                       # 0-based, like bcf::Record::pos()
+    id: str
+    alleles: List[bytes]
+    info: Dict[str, List[Union[int, str]]]
+
+
+def parse_vcf_record_line(line: str, label_to_index: Dict[str, int]) -> CandidateRecord:
+    f = line.rstrip("\n").split("\t")
+    info: Dict[str, List[Union[int, str]]] = {}
+    for item in f[7].split(";"):
+        if not item or item == ".":
+            continue
+        if "=" not in item:
+            info[item] = []
+            continue
+        key, val = item.split("=", 1)
+        info[key] = [int(v) if v.lstrip("-").isdigit() else v for v in val.split(",")]
+    return CandidateRecord(label_to_index[f[0]], int(f[1]) - 1, f[2], [f[3].encode()] + [a.encode() for a in f[4].split(",")], info)
+
+
+@dataclass(frozen=True)
+class RecBreakend:  # Breakend { segment: GenomeSegment { chrom_index, range }, dir }
+    chrom_index: int
+    start: int
+    end: int
+    dir: str
+
+
+@dataclass
+class RecBreakpoint:
+    breakend1: RecBreakend
+    breakend2: RecBreakend
+    insert_seq: bytes                      # InsertInfo::Seq / NoInsert
+    breakend1_neighbor: Optional[Tuple[int, int]] = None   # (cluster_index, breakend_index)
+    breakend2_neighbor: Optional[Tuple[int, int]] = None
+
+    def is_indel(self) -> bool:            # src/breakpoint.rs:251-262
+        return self.breakend1.chrom_index == self.breakend2.chrom_index and \
+            self.breakend1.dir == LEFT_ANCHOR and self.breakend2.dir == RIGHT_ANCHOR
+
+    def deletion_size(self) -> Optional[int]:  # :264-273
+        return max(self.breakend2.start - self.breakend1.start, 0) if self.is_indel() else None
+
+
+@dataclass
+class AnnotatedRefinedSV:
+    id: SVUniqueIdData
+    bp: RecBreakpoint
+    breakend1_homology_seq: bytes
+    contig_pos_before_breakend1: int
+    contig_map: List[int]
+
+
+def _first(info, key, default=None):
+    v = info.get(key)
+    return v[0] if v else default
+
+
+def _neighbor(info, key) -> Optional[Tuple[int, int]]:  # parse_breakend_neighbor_info (:300-329): "cluster:breakend"
+    v = _first(info, key)
+    if v is None:
+        return None
+    a, b = str(v).split(":")
+    return int(a), int(b)
+
+
+def process_record_to_anno_refined_sv(label_to_index: Dict[str, int], rec: CandidateRecord) -> Optional[AnnotatedRefinedSV]:
+    """:334-552.  DEL / INS records give an indel breakpoint (breakend ranges widened by the homology length); of a BND pair
+    only the breakend-1 record is used, its mate comes from the alt allele."""
+    sv_id, is_breakend1 = get_sv_id_from_label(rec.id)
+    if len(rec.alleles) != 2:
+        raise ValueError(f"Unexpected allele count in sample candidate SV input {len(rec.alleles)}")
+    alt = rec.alleles[1]
+    svtype = str(_first(rec.info, "SVTYPE"))
+    homlen = int(_first(rec.info, "HOMLEN", 0))
+    homseq = str(_first(rec.info, "HOMSEQ", "")).encode()
+    assert homlen == len(homseq)
+    contig_pos = int(_first(rec.info, CONTIG_POS_INFO_KEY))
+    overlapping = [int(x) for x in rec.info.get(OVERLAP_ASM_INFO_KEY, [])]
+    contig_map = overlapping if overlapping else [sv_id.assembly_index]
+    if svtype in ("DEL", "INS"):
+        assert is_breakend1 is None
+        end = int(_first(rec.info, "END")) - 1
+        be1 = RecBreakend(rec.chrom_index, rec.pos, rec.pos + homlen + 1, LEFT_ANCHOR)
+        be2 = RecBreakend(rec.chrom_index, end, end + homlen + 1, RIGHT_ANCHOR)
+        insert_seq = str(_first(rec.info, "INSSEQ", "")).encode() if alt == b"<DEL>" else alt[1:]
+        return AnnotatedRefinedSV(sv_id, RecBreakpoint(be1, be2, insert_seq), homseq, contig_pos, contig_map)
+    if svtype == "BND":
+        assert is_breakend1 is not None
+        if not is_breakend1:
+            return None
+        b = parse_bnd_alt_allele(label_to_index, alt, homlen)
+        p1 = rec.pos if b.breakend1_direction == LEFT_ANCHOR else rec.pos - 1
+        be1 = RecBreakend(rec.chrom_index, p1, p1 + homlen + 1, b.breakend1_direction)
+        be2 = RecBreakend(b.breakend2_chrom_index, b.breakend2_pos, b.breakend2_pos + homlen + 1, b.breakend2_direction)
+        bp = RecBreakpoint(be1, be2, b.insert_seq, _neighbor(rec.info, BND0_NEIGHBOR_INFO_KEY), _neighbor(rec.info, BND1_NEIGHBOR_INFO_KEY))
+        return AnnotatedRefinedSV(sv_id, bp, homseq, contig_pos, contig_map)
+    raise ValueError(f"Unexpected SV type: {svtype}")

@@ -199,3 +199,35 @@ def test_parse_bnd_alt_allele_reference_vectors():
     assert (info.breakend1_direction, info.breakend2_direction, info.breakend2_pos, info.insert_seq) == (RIGHT_ANCHOR, RIGHT_ANCHOR, 488, b"GA")
     with pytest.raises(ValueError):
         parse_bnd_alt_allele({"chr1": 0}, b"TCT", 0)
+
+
+def test_candidate_records_to_refined_svs():
+    """process_bcf_record_to_anno_refine_sv (get_refined_svs.rs:334-552) on the record content a candidate VCF carries."""
+    from sawfish_b200 import candidate_sv as CS
+    l2i = {"chr1": 0, "chr20": 1}
+    sv_id, be = CS.get_sv_id_from_label("sawfish:0:12:1:0")
+    assert (sv_id.sample_index, sv_id.cluster_index, sv_id.assembly_index, sv_id.alignment_index, be) == (0, 12, 1, 0, None)
+    assert CS.get_sv_id_from_label("sawfish:0:12:1:0:1")[1] is False and CS.get_sv_id_from_label("sawfish:0:12:1:0:0")[1] is True
+    lines = [
+        # symbolic deletion with 3 bases of breakend homology and a small insertion at the junction
+        "chr20\t1001\tsawfish:0:3:0:0\tA\t<DEL>\t.\t.\tSVTYPE=DEL;END=1501;SVLEN=500;HOMLEN=3;HOMSEQ=CAG;INSSEQ=TT;CONTIG_POS=1499",
+        # sequence-resolved insertion, contig shared with assembly 1
+        "chr20\t2001\tsawfish:0:4:0:0\tG\tGACGTACGT\t.\t.\tSVTYPE=INS;END=2001;SVLEN=8;CONTIG_POS=1500;OVERLAP_ASM=0,1",
+        # breakend pair: only breakend 1 is converted
+        "chr1\t5001\tsawfish:0:5:0:0:0\tT\tTCT]chr20:9000]\t.\t.\tSVTYPE=BND;HOMLEN=2;HOMSEQ=AC;CONTIG_POS=1498;BND0_NEIGHBOR=7:1",
+        "chr20\t9000\tsawfish:0:5:0:0:1\tC\tC]chr1:5001]\t.\t.\tSVTYPE=BND;HOMLEN=2;HOMSEQ=AC;CONTIG_POS=1498",
+    ]
+    recs = [CS.parse_vcf_record_line(x, l2i) for x in lines]
+    d = CS.process_record_to_anno_refined_sv(l2i, recs[0])
+    assert (d.bp.breakend1, d.bp.breakend2) == (CS.RecBreakend(1, 1000, 1004, CS.LEFT_ANCHOR), CS.RecBreakend(1, 1500, 1504, CS.RIGHT_ANCHOR))
+    assert (d.bp.insert_seq, d.breakend1_homology_seq, d.contig_pos_before_breakend1, d.contig_map) == (b"TT", b"CAG", 1499, [0])
+    assert d.bp.is_indel() and d.bp.deletion_size() == 500
+    i = CS.process_record_to_anno_refined_sv(l2i, recs[1])
+    assert (i.bp.breakend1.start, i.bp.breakend2.start, i.bp.insert_seq, i.contig_map) == (2000, 2000, b"ACGTACGT", [0, 1])
+    assert i.bp.deletion_size() == 0
+    b = CS.process_record_to_anno_refined_sv(l2i, recs[2])
+    assert b.bp.breakend1 == CS.RecBreakend(0, 5000, 5003, CS.LEFT_ANCHOR)
+    assert b.bp.breakend2 == CS.RecBreakend(1, 8997, 9000, CS.LEFT_ANCHOR)        # same orientation: shifted left by homlen
+    assert (b.bp.insert_seq, b.bp.breakend1_neighbor, b.bp.breakend2_neighbor) == (b"CT", (7, 1), None)
+    assert not b.bp.is_indel() and b.bp.deletion_size() is None
+    assert CS.process_record_to_anno_refined_sv(l2i, recs[3]) is None
