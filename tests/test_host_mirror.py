@@ -36,3 +36,14 @@ def test_sawfish_clip_truncation():
     # f64 -> i32 truncation of 0.4 * len (reference src/wfa2_utils.rs:111-115)
     assert sawfish_clip(6, 10) == 2 and sawfish_clip(500, 500) == 200 and sawfish_clip(7, 1000) == 2
     assert sawfish_clip(1, 1) == 0
+
+
+def test_prob_utils_reference_vectors():
+    """The reference's unit tests of the phred / normalisation helpers the genotype chain uses (src/prob_utils.rs:72-93)."""
+    import math
+    from sawfish_b200 import score_sv as S
+    assert S._rust_round(S.error_prob_to_phred(0.001)) == 30                # test_error_prob_to_qphred
+    assert S.ln_error_prob_to_qphred(math.log(0.001)) == 30                 # test_ln_error_prob_to_qphred
+    x = [math.log(v) for v in (0.001, 0.001, 0.002, 0.001)]
+    assert S.normalize_ln_distro(x) == 2                                    # test_normalize_ln_distro
+    assert math.isclose(x[0], 0.2, rel_tol=0, abs_tol=4 * 2.0 ** -52) and math.isclose(x[2], 0.4, rel_tol=0, abs_tol=4 * 2.0 ** -52)
