@@ -203,3 +203,49 @@ def get_read_breakend_flank_range(pos: int, cigar: Sequence[Cigar], read_len: in
     full_start = flank_end - READ_SUPPORT_FLANK_SIZE
     flank_start, start_trunc = (0, -full_start) if full_start < 0 else (full_start, 0)
     return flank(flank_start, flank_end, start_trunc, 0)
+
+
+# ------------------------------------------------------------------------------------------------ allele (pattern) side
+def convert_breakend_to_ref_flank_range(breakend_dir: str, breakend_range: Tuple[int, int], chrom_len: int) -> Optional[Tuple[int, int]]:
+    """convert_breakend_to_ref_flank (src/score_sv/mod.rs:36-78): the reference range the ref-allele flank is cut from.
+    Left anchor: the 500 bases after the breakend segment; right anchor: the 500 bases before its start plus that base
+    (GenomeSegment::asymmetric_expand_by clips at the chromosome ends)."""
+    if breakend_dir == LEFT_ANCHOR:
+        start = breakend_range[1]
+        end = min(breakend_range[1] + READ_SUPPORT_FLANK_SIZE, chrom_len)
+    else:
+        end = min(breakend_range[0] + 1, chrom_len)
+        start = max(breakend_range[0] - READ_SUPPORT_FLANK_SIZE, 0)
+    if start < 0 or end <= start or end - start < MIN_READ_SUPPORT_FLANK_SIZE:
+        return None
+    return start, end
+
+
+def convert_breakend_to_haplotype_contig_flank_range(contig_len: int, ref_offset: int, cigar: Sequence[Cigar], breakend_dir: str,
+                                                     breakend_range: Tuple[int, int],
+                                                     assembly_range: Optional[Tuple[int, int]] = None) -> Optional[Tuple[int, int]]:
+    """convert_breakend_to_haplotype_contig_flank_seq (:106-222): the contig range the alt-allele flank is cut from; the
+    contig alignment plays the role the read alignment plays in get_read_breakend_flank_range, without the 10-base anchor
+    offset and without truncation (a flank that would leave the contig is dropped)."""
+    homology_len = breakend_range[1] - breakend_range[0] - 1
+
+    def flank(start, end):
+        if start < 0 or end >= contig_len or end - start < MIN_READ_SUPPORT_FLANK_SIZE:
+            return None
+        return start, end
+
+    if breakend_dir == LEFT_ANCHOR:
+        ref_target_pos = breakend_range[0]
+        anchor = assembly_range[0] if assembly_range is not None else ref_target_pos
+        m = get_alignment_closest_to_target_ref_pos(ref_offset, cigar, anchor, TARGET_OR_LOWER)
+        if m is None:
+            return None
+        flank_start = m[0] + (ref_target_pos - m[1]) + 1 + homology_len
+        return flank(flank_start, flank_start + READ_SUPPORT_FLANK_SIZE)
+    ref_target_pos = breakend_range[1]
+    anchor = assembly_range[1] if assembly_range is not None else ref_target_pos
+    m = get_alignment_closest_to_target_ref_pos(ref_offset, cigar, anchor, TARGET_OR_HIGHER)
+    if m is None:
+        return None
+    flank_end = m[0] + (ref_target_pos - m[1]) - homology_len
+    return flank(flank_end - READ_SUPPORT_FLANK_SIZE, flank_end)

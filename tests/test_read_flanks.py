@@ -81,3 +81,100 @@ def test_read_breakend_flank_range_rules():
     f = RF.get_read_breakend_flank_range(pos, cigar, L, RF.LEFT_ANCHOR, (11_000, 11_001), assembly_range=(10_900, 11_200))
     assert f.range == (1001, 1501)
     assert RF.get_read_breakend_flank_range(pos, cigar, L, RF.LEFT_ANCHOR, (11_000, 11_001), assembly_range=(10_995, 11_200)) is None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# One locus end to end from ALIGNMENTS (not pre-cut flanks): reference, an assembled alt contig with its alignment, reads
+# of both haplotypes with theirs -> read filter -> read / allele flank ranges -> pair batch -> scores -> AD -> genotype.
+import numpy as np  # noqa: E402
+import pytest  # noqa: E402
+
+from sawfish_b200 import score_sv as S  # noqa: E402
+from sawfish_b200 import synth  # noqa: E402
+
+
+def _locus_pairs(seed, gt):
+    rng = np.random.default_rng(seed)
+    ref = synth.random_seq(rng, 8000)
+    d0, dl = 4000, 300                                            # deletion of ref[4000:4300)
+    contig = np.concatenate([ref[2500:d0], ref[d0 + dl:5800]])    # assembled alt haplotype
+    contig_aln = (2500, [("=", 1500), ("D", dl), ("=", 1500)])
+    be1 = (RF.LEFT_ANCHOR, (d0 - 1, d0))                          # VCF POS = base before the deletion
+    be2 = (RF.RIGHT_ANCHOR, (d0 + dl - 1, d0 + dl))               # END - 1, see candidate_sv.process_record_to_anno_refined_sv
+    asm = (3900, 4400)
+    b = S.PairBatchBuilder()
+    truth = {}
+    for ri in range(30):
+        from_alt = rng.random() < (0.0, 0.5, 1.0)[gt]
+        start = int(rng.integers(2600, 3300))
+        if from_alt:
+            hap = np.concatenate([ref[start:d0], ref[d0 + dl:start + 2200]])
+            cigar = [("=", d0 - start), ("D", dl), ("=", len(hap) - (d0 - start))]
+        else:
+            hap = ref[start:start + 2200]
+            cigar = [("=", len(hap))]
+        read = hap.copy()                                          # substitutions only: the alignment stays valid
+        for p in rng.integers(0, len(read), 2):
+            read[int(p)] = (read[int(p)] + 1) if read[int(p)] != ord("T") else ord("A")
+        read = np.frombuffer(bytes(bytearray(read.tolist())).translate(bytes.maketrans(b"BDHU", b"CGTA")), np.uint8)
+        mcig = [("M", n) if op == "=" else (op, n) for op, n in cigar]
+        if not RF.passes_read_filter(60, start, mcig, read.tobytes(), ref.tobytes()):
+            continue
+        qname = f"read{ri:03d}"
+        truth[qname] = from_alt
+        for bi, (bdir, brange) in enumerate((be1, be2)):
+            ref_rng = RF.convert_breakend_to_ref_flank_range(bdir, brange, len(ref))
+            alt_std = RF.convert_breakend_to_haplotype_contig_flank_range(len(contig), contig_aln[0], contig_aln[1], bdir, brange)
+            alt_ext = RF.convert_breakend_to_haplotype_contig_flank_range(len(contig), contig_aln[0], contig_aln[1], bdir, brange, asm)
+            for reg, arng, alt_rng in ((S.STANDARD, None, alt_std), (S.ASM_REGION_EDGE, asm, alt_ext)):
+                f = RF.get_read_breakend_flank_range(start, mcig, len(read), bdir, brange, arng)
+                if f is None:
+                    continue
+                # the ref allele has no second registration: its standard flank is scored against both read registrations
+                # (ref_flank_seqs.breakend_flanks[breakend_index][standard_registration_index], src/score_sv/mod.rs:842-846)
+                ref_seq = ref[ref_rng[0]:ref_rng[1]] if ref_rng is not None else None
+                alt_seq = contig[alt_rng[0]:alt_rng[1]] if alt_rng is not None else None
+                b.add_read_flank(0, qname, bi, reg, S.ReadFlank(read[f.range[0]:f.range[1]], f.start_truncation, f.end_truncation),
+                                 ref_seq, alt_seq, [])
+    return b, truth
+
+
+def _genotype(b, align_fn):
+    arena, pairs = b.finish()
+    scores = align_fn(arena, pairs)
+    locus = S.scatter_scores(b.slots, scores, {0: []})
+    ad = S.set_allele_depth_counts(locus.get(0, {}), sv_haplotype_index=0, overlapping_haplotype_index=None,
+                                   is_alt_on_top_haplotype_rank=True, on_multiple_sample_haplotypes=False, read_to_hap={})
+    samples, qual = S.get_sv_qualities_from_allele_counts([ad])
+    return ad, samples[0], qual, len(pairs), scores
+
+
+def _oracle_fn():
+    from oracle import oracle as O
+
+    def f(arena, pairs):
+        sc, st, *_ = O.align_batch(O.CONSENSUS, arena, pairs.astype(O.PAIR_DTYPE), want_ops=True, n_threads=4)
+        assert (st == 0).all()
+        return sc
+    return f
+
+
+@pytest.mark.parametrize("gt", [0, 1, 2])
+def test_locus_from_alignments_recovers_the_genotype(gt):
+    b, truth = _locus_pairs(100 + gt, gt)
+    ad, sample, qual, n_pairs, _ = _genotype(b, _oracle_fn())
+    n_alt = sum(truth.values())
+    assert n_pairs > 60
+    assert ad[1] >= 0.8 * n_alt and ad[0] >= 0.8 * (len(truth) - n_alt)   # reads vote for the haplotype they came from
+    assert sample.gt == (S.Genotype.Ref, S.Genotype.Het, S.Genotype.Hom)[gt]
+
+
+@pytest.mark.gpu
+def test_locus_from_alignments_gpu_equals_oracle():
+    from sawfish_b200.batch import AlignContext
+    ctx = AlignContext(0)
+    b, _ = _locus_pairs(101, 1)
+    want = _genotype(b, _oracle_fn())
+    got = _genotype(b, S.gpu_align_fn(ctx))
+    assert (got[4] == want[4]).all() and got[0] == want[0] and got[2] == want[2]
+    ctx.close()
