@@ -260,14 +260,17 @@ def get_candidate_sv_contig_info(path: str) -> List[List[ClusterAssembly]]:
         contig_seq = get_simplified_dna_seq(rec.seq)
         ca.contig_alignments.append(ClusterAssemblyAlignment(contig_seq, rec.tid, SimpleAlignment(rec.pos, list(rec.cigar)), hq, True))
         if SA_AUX_TAG in rec.aux:
-            for word in rec.aux[SA_AUX_TAG].split(";"):
-                if not word:
+            # every other segment of the contig, in read (sequencing) order — get_seq_order_read_split_segments
+            from .read_flanks import get_seq_order_read_split_segments
+            segs = get_seq_order_read_split_segments(chrom_index, rec.tid, rec.pos, bool(rec.flag & BAM_FREVERSE), rec.cigar, rec.mapq,
+                                                     rec.aux[SA_AUX_TAG])
+            for seg in segs:
+                if seg.from_primary_bam_record:
                     continue
-                chrom, pos1, strand, cig, _mapq, _nm = word.split(",")
-                fwd = strand == "+"
                 seq2, hq2 = contig_seq, hq
-                if not fwd:  # rev_comp_in_place + IntRange::reverse(len): [len - end, len - start)
+                if not seg.is_fwd_strand:  # rev_comp_in_place + IntRange::reverse(len): [len - end, len - start)
                     seq2 = rev_comp(contig_seq)
                     hq2 = (len(contig_seq) - hq[1], len(contig_seq) - hq[0])
-                ca.contig_alignments.append(ClusterAssemblyAlignment(seq2, chrom_index[chrom], SimpleAlignment(int(pos1) - 1, cigar_from_string(cig)), hq2, fwd))
+                ca.contig_alignments.append(ClusterAssemblyAlignment(seq2, seg.chrom_index, SimpleAlignment(seg.pos, list(seg.cigar)), hq2,
+                                                                     seg.is_fwd_strand))
     return sample_assemblies

@@ -249,3 +249,118 @@ def convert_breakend_to_haplotype_contig_flank_range(contig_len: int, ref_offset
         return None
     flank_end = m[0] + (ref_target_pos - m[1]) - homology_len
     return flank(flank_end - READ_SUPPORT_FLANK_SIZE, flank_end)
+
+
+# ------------------------------------------------------------------------------------------------ split reads
+# For breakpoint (two-region) SVs a read reaches the locus as several BAM records; a record's flank is only used for a
+# breakend when THAT record is the split segment next to the breakend and its neighbour in read order sits on the mate
+# breakend (src/score_sv/mod.rs:484-640).
+def get_read_clip_positions(cigar: Sequence[Cigar], ignore_hard_clip: bool) -> Tuple[int, int, int]:
+    """(first position after the left clip, first position of the right clip, read length) —
+    lib/rust-vc-utils/src/bam_utils/cigar/mod.rs:85-116."""
+    read_pos = left_clip = right_clip = 0
+    left = True
+    for c in cigar:
+        op, n = c
+        if op == "S" or (op == "H" and not ignore_hard_clip):
+            if left:
+                left_clip += n
+            else:
+                right_clip += n
+        elif op != "H":
+            left = False
+        read_pos += _read_advance(c, ignore_hard_clip)
+    return left_clip, read_pos - right_clip, read_pos
+
+
+@dataclass
+class SeqOrderSplitReadSegment:  # lib/rust-vc-utils/src/bam_utils/split_read.rs:14-33
+    seq_order_read_start: int
+    seq_order_read_end: int
+    chrom_index: int
+    pos: int
+    is_fwd_strand: bool
+    cigar: List[Cigar]
+    mapq: int
+    from_primary_bam_record: bool
+
+
+def get_seq_order_read_split_segments(label_to_index, tid: int, pos: int, is_reverse: bool, cigar: Sequence[Cigar], mapq: int,
+                                      sa_tag: Optional[str]) -> List[SeqOrderSplitReadSegment]:
+    """All alignment segments of a read (this record + its SA tag) ordered by their start in SEQUENCING order of the read
+    (split_read.rs:56-161).  Hard clips count (ignore_hard_clip = false): supplementary records are hard-clipped."""
+    from .simple_alignment import cigar_from_string
+
+    def seq_order(read_start, read_end, read_size, fwd):
+        return (read_start, read_end) if fwd else (read_size - read_end, read_size - read_start)
+
+    rs, re_, size = get_read_clip_positions(cigar, False)
+    s, e = seq_order(rs, re_, size, not is_reverse)
+    segs = [SeqOrderSplitReadSegment(s, e, tid, pos, not is_reverse, list(cigar), mapq, True)]
+    if sa_tag:
+        for word in sa_tag.split(";"):
+            if not word:
+                continue
+            rname, pos1, strand, cig, mq, _nm = word.split(",")
+            c2 = cigar_from_string(cig)
+            assert any(op in "M=X" for op, _ in c2), "Bam record split segment is unaligned"
+            rs, re_, size2 = get_read_clip_positions(c2, False)
+            assert size2 == size
+            fwd = strand == "+"
+            s, e = seq_order(rs, re_, size2, fwd)
+            segs.append(SeqOrderSplitReadSegment(s, e, label_to_index[rname], int(pos1) - 1, fwd, c2, int(mq), False))
+        segs.sort(key=lambda x: x.seq_order_read_start)  # stable, like sort_by_key
+    for x in segs:
+        assert x.seq_order_read_start < x.seq_order_read_end, "Can't parse consistent split read information from SA tag"
+    return segs
+
+
+@dataclass
+class BreakendMatchSplitReadInfo:  # src/score_sv/mod.rs:480-483
+    seq_order_read_split_segments: List[Tuple[int, int, int]]   # (chrom_index, start, end) per segment, read order
+    primary_split_segment_index: int
+
+
+def get_split_read_info(label_to_index, tid, pos, is_reverse, cigar, mapq, sa_tag, single_region_refinement: bool) -> Optional[BreakendMatchSplitReadInfo]:
+    """:602-633.  None = no check needed (indel-like SV, or the read is not split)."""
+    if single_region_refinement or not sa_tag:
+        return None
+    out, primary = [], 0
+    for i, seg in enumerate(get_seq_order_read_split_segments(label_to_index, tid, pos, is_reverse, cigar, mapq, sa_tag)):
+        if seg.from_primary_bam_record:
+            primary = i
+        out.append((seg.chrom_index, seg.pos, seg.pos + sum(n for op, n in seg.cigar if op in "MDN=X")))
+    return BreakendMatchSplitReadInfo(out, primary)
+
+
+def get_segment_breakend_distance(segment: Tuple[int, int, int], breakend_chrom: int, breakend_dir: str, breakend_start: int) -> Optional[int]:
+    """:485-500: a left-anchored breakend is matched by a segment END, a right-anchored one by a segment START."""
+    if segment[0] != breakend_chrom:
+        return None
+    return abs((segment[2] if breakend_dir == LEFT_ANCHOR else segment[1]) - breakend_start)
+
+
+def is_segment_breakend_match(segment_index: int, breakend, info: BreakendMatchSplitReadInfo) -> bool:
+    """:504-522: no other split segment of the read is closer to the breakend.  breakend = (chrom, dir, range start)."""
+    d = [get_segment_breakend_distance(s, *breakend) for s in info.seq_order_read_split_segments]
+    if d[segment_index] is None:
+        return False
+    return all(x >= d[segment_index] for x in d if x is not None)
+
+
+def does_read_segment_match_breakend(is_reverse: bool, target_breakend, mate_breakend, info: BreakendMatchSplitReadInfo) -> bool:
+    """:526-565: this record is the closest segment to the target breakend AND the adjacent segment in read order (the next
+    one for a left anchor on a forward record, the previous one otherwise) is the closest to the mate breakend."""
+    t = info.primary_split_segment_index
+    if not is_segment_breakend_match(t, target_breakend, info):
+        return False
+    is_plus_one = (target_breakend[1] == LEFT_ANCHOR) ^ is_reverse
+    if is_plus_one:
+        if t + 1 >= len(info.seq_order_read_split_segments):
+            return False
+        mate_index = t + 1
+    else:
+        if t == 0:
+            return False
+        mate_index = t - 1
+    return is_segment_breakend_match(mate_index, mate_breakend, info)

@@ -178,3 +178,41 @@ def test_locus_from_alignments_gpu_equals_oracle():
     got = _genotype(b, S.gpu_align_fn(ctx))
     assert (got[4] == want[4]).all() and got[0] == want[0] and got[2] == want[2]
     ctx.close()
+
+
+def test_seq_order_read_split_segments_reference_vectors():
+    """lib/rust-vc-utils/src/bam_utils/split_read.rs:202-237."""
+    l2i = {"chr0": 0, "chr1": 1, "chr2": 2}
+
+    def flat(segs):
+        from sawfish_b200.simple_alignment import cigar_to_string
+        return [(s.seq_order_read_start, s.seq_order_read_end, s.chrom_index, s.pos, s.is_fwd_strand, cigar_to_string(s.cigar),
+                 s.from_primary_bam_record) for s in segs]
+
+    got = RF.get_seq_order_read_split_segments(l2i, 2, 9, False, cg("10S5M5S"), 60, None)
+    assert flat(got) == [(10, 15, 2, 9, True, "10S5M5S", True)]
+    sa = "chr0,20,-,5M15S,60,0;chr0,100,+,5S5M10S,60,0;chr1,200,-,15S5M,60,0;"
+    got = RF.get_seq_order_read_split_segments(l2i, 2, 9, False, cg("10S5M5S"), 60, sa)
+    assert flat(got) == [(0, 5, 1, 199, False, "15S5M", False), (5, 10, 0, 99, True, "5S5M10S", False),
+                         (10, 15, 2, 9, True, "10S5M5S", True), (15, 20, 0, 19, False, "5M15S", False)]
+    assert all(s.mapq == 60 for s in got)
+
+
+def test_split_read_segment_matches_its_breakend():
+    """A translocation-like junction chr0:5000 (left anchor) -> chr1:9000 (right anchor) and a read split across it."""
+    l2i = {"chr0": 0, "chr1": 1}
+    be1, be2 = (0, RF.LEFT_ANCHOR, 4999), (1, RF.RIGHT_ANCHOR, 9000)
+    # primary record = first 1 000 bases on chr0 ending at the junction; supplementary = last 1 000 bases on chr1
+    info = RF.get_split_read_info(l2i, 0, 4000, False, cg("1000M1000S"), 60, "chr1,9001,+,1000S1000M,60,0;", False)
+    assert info.primary_split_segment_index == 0 and info.seq_order_read_split_segments == [(0, 4000, 5000), (1, 9000, 10000)]
+    assert RF.does_read_segment_match_breakend(False, be1, be2, info)         # this record carries breakend 1 ...
+    assert not RF.does_read_segment_match_breakend(False, be2, be1, info)     # ... but not breakend 2
+    # the same read seen from its supplementary record
+    info2 = RF.get_split_read_info(l2i, 1, 9000, False, cg("1000H1000M"), 60, "chr0,4001,+,1000M1000S,60,0;", False)
+    assert info2.primary_split_segment_index == 1
+    assert RF.does_read_segment_match_breakend(False, be2, be1, info2) and not RF.does_read_segment_match_breakend(False, be1, be2, info2)
+    # a third, closer segment elsewhere on chr0 steals breakend 1
+    info3 = RF.get_split_read_info(l2i, 0, 3000, False, cg("500M2500S"), 60, "chr0,4501,+,500S500M2000S,60,0;chr1,9001,+,2000S1000M,60,0;", False)
+    assert not RF.does_read_segment_match_breakend(False, be1, be2, info3)
+    assert RF.get_split_read_info(l2i, 0, 4000, False, cg("2000M"), 60, None, False) is None       # not split: no check
+    assert RF.get_split_read_info(l2i, 0, 4000, False, cg("1000M1000S"), 60, "chr1,9001,+,1000S1000M,60,0;", True) is None
