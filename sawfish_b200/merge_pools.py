@@ -190,3 +190,42 @@ def get_haplotype_merge_pools_sequential(haplotypes: Sequence[MergeHaplotype], s
         if len(pool) > 1:
             pool.sort(key=lambda h: (-haplotypes[h].supporting_read_count, -len(haplotypes[h].contig_seq)))
     return pools
+
+
+# ---------------------------------------------------------------------------------------------- multi-region SV groups
+def get_multi_region_merge_pools(groups: Sequence[MergeHaplotype], score_fn: ScoreFn) -> Tuple[List[List[int]], Dict[str, int]]:
+    """The pooling step of merge_duplicated_candidates for multi-region (breakpoint) SV groups
+    (src/joint_call/merge_haplotypes/multi_region/merge_pools.rs:150-215), in the same two-phase form: every sv group holds
+    exactly one SV and one haplotype; two groups are duplicates when their breakpoints are EQUAL (:86-88) or the merge aligner
+    says so (:12-75, same base / query rule and 0.97 threshold as the single-region case); no exclusion sets here."""
+    n = len(groups)
+    need: Dict[Tuple[int, int], int] = {}
+    batch: List[Tuple[bytes, bytes]] = []
+    for g1 in range(n):
+        for g2 in range(g1 + 1, n):
+            if list(groups[g1].breakpoints[:1]) == list(groups[g2].breakpoints[:1]):
+                continue
+            need[(g1, g2)] = len(batch)
+            batch.append(merge_alignment_pair(groups[g1], groups[g2]))
+    scores = score_fn(batch)
+    dup = {k: (scores[i] / len(batch[i][1])) >= MIN_MERGE_NORM_SCORE for k, i in need.items()}
+    pools: List[List[int]] = [[x] for x in range(n)]
+    used = 0
+    for g1 in range(n):
+        if not pools[g1]:
+            continue
+        for g2 in range(g1 + 1, n):
+            if not pools[g2]:
+                continue
+            if (g1, g2) in dup:
+                is_dup = dup[(g1, g2)]
+                used += 1
+            else:
+                is_dup = True
+            if is_dup:
+                pools[g1].extend(pools[g2])
+                pools[g2] = []
+    for pool in pools:
+        if len(pool) > 1:
+            pool.sort(key=lambda g: (-groups[g].supporting_read_count, -len(groups[g].contig_seq)))
+    return pools, {"alignments_batched": len(batch), "alignments_consumed": used}

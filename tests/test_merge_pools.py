@@ -117,3 +117,35 @@ def test_gpu_pools_equal_oracle_pools():
         total += counters["alignments_batched"]
     assert total > 0
     ctx.close()
+
+
+def test_multi_region_pools_two_phase_equals_sequential():
+    """multi_region/merge_pools.rs:150-215: greedy pooling of one-haplotype sv groups, breakpoint equality or alignment."""
+    rng = np.random.default_rng(47)
+    for _ in range(4):
+        haps, _lists = synth_pool(rng, n_samples=int(rng.integers(3, 7)))
+        groups = [h for h in haps if h.breakpoints]
+        got, counters = MP.get_multi_region_merge_pools(groups, lambda pairs: [oracle_score(b, q) for b, q in pairs])
+        # the reference's control flow, one alignment call inside the loop
+        n = len(groups)
+        want = [[x] for x in range(n)]
+        for g1 in range(n):
+            if not want[g1]:
+                continue
+            for g2 in range(g1 + 1, n):
+                if not want[g2]:
+                    continue
+                if groups[g1].breakpoints[:1] == groups[g2].breakpoints[:1]:
+                    is_dup = True
+                else:
+                    base, query = MP.merge_alignment_pair(groups[g1], groups[g2])
+                    is_dup = oracle_score(base, query) / len(query) >= 0.97
+                if is_dup:
+                    want[g1].extend(want[g2])
+                    want[g2] = []
+        for p in want:
+            if len(p) > 1:
+                p.sort(key=lambda g: (-groups[g].supporting_read_count, -len(groups[g].contig_seq)))
+        assert got == want
+        assert sorted(g for p in got for g in p) == list(range(n))
+        assert counters["alignments_consumed"] <= counters["alignments_batched"]
