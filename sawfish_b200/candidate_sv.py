@@ -181,3 +181,155 @@ def process_record_to_anno_refined_sv(label_to_index: Dict[str, int], rec: Candi
         bp = RecBreakpoint(be1, be2, b.insert_seq, _neighbor(rec.info, BND0_NEIGHBOR_INFO_KEY), _neighbor(rec.info, BND1_NEIGHBOR_INFO_KEY))
         return AnnotatedRefinedSV(sv_id, bp, homseq, contig_pos, contig_map)
     raise ValueError(f"Unexpected SV type: {svtype}")
+
+
+# ---------------------------------------------------------------------------------------------- BCF2 (VCF spec v4.3, section 6)
+# `candidate.sv.bcf` is written and read through htslib in the reference (get_anno_refined_svs, :554-601).  htslib is not in
+# this image: the subset of BCF2 those records use (site-only records: CHROM, POS, ID, REF/ALT, FILTER, INFO with Integer /
+# String / Flag values, no FORMAT block) is decoded / encoded here directly.  Parity of the decoder with htslib-written files
+# is UNPINNED (no candidate.sv.bcf ships with the reference); it is checked against this module's own encoder and against the
+# byte layout of the specification.
+import gzip as _gzip  # noqa: E402
+import struct as _struct  # noqa: E402
+import re as _re  # noqa: E402
+
+CANDIDATE_SV_FILENAME = "candidate.sv.bcf"  # src/filenames.rs
+_BCF_INT = {1: ("b", 1, -128), 2: ("h", 2, -32768), 3: ("i", 4, -2147483648)}  # type code -> (struct fmt, size, missing)
+
+
+def _typed_int_type(vals) -> int:
+    lo, hi = (min(vals), max(vals)) if vals else (0, 0)
+    if -120 <= lo and hi <= 127:
+        return 1
+    if -32760 <= lo and hi <= 32767:
+        return 2
+    return 3
+
+
+def _enc_desc(count: int, typ: int) -> bytes:
+    if count < 15:
+        return bytes([(count << 4) | typ])
+    t = _typed_int_type([count])
+    return bytes([0xF0 | typ, (1 << 4) | t]) + _struct.pack("<" + _BCF_INT[t][0], count)
+
+
+def _enc_ints(vals) -> bytes:
+    t = _typed_int_type(vals)
+    return _enc_desc(len(vals), t) + _struct.pack(f"<{len(vals)}{_BCF_INT[t][0]}", *vals)
+
+
+def _enc_str(s: bytes) -> bytes:
+    return _enc_desc(len(s), 7) + s if s else bytes([0x07])
+
+
+def write_candidate_bcf(path: str, chroms, records: List[CandidateRecord], info_types: Dict[str, str]) -> None:
+    """records' chrom_index refers to `chroms` [(name, length)]; info_types: key -> "Integer" | "String" | "Flag"."""
+    from .contig_bam import _bgzf_write
+    keys = list(info_types)
+    text = "##fileformat=VCFv4.2\n##FILTER=<ID=PASS,Description=\"All filters passed\">\n"
+    for k in keys:
+        number = "0" if info_types[k] == "Flag" else "."
+        text += f"##INFO=<ID={k},Number={number},Type={info_types[k]},Description=\"{k}\">\n"
+    for name, ln in chroms:
+        text += f"##contig=<ID={name},length={ln}>\n"
+    text += "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n"
+    tb = text.encode() + b"\0"
+    out = [b"BCF\x02\x02", _struct.pack("<I", len(tb)), tb]
+    dict_index = {"PASS": 0, **{k: i + 1 for i, k in enumerate(keys)}}
+    for r in records:
+        rlen = len(r.alleles[0])
+        end = r.info.get("END")
+        if end:
+            rlen = int(end[0]) - r.pos
+        body = _struct.pack("<iiifII", r.chrom_index, r.pos, rlen, float("nan"), (len(r.alleles) << 16) | len(r.info), 0)
+        body = body[:12] + _struct.pack("<I", 0x7F800001) + body[16:]  # QUAL missing
+        body += _enc_str(r.id.encode())
+        for a in r.alleles:
+            body += _enc_str(a)
+        body += bytes([0x00])  # FILTER: empty vector
+        for k, v in r.info.items():
+            body += _enc_ints([dict_index[k]])
+            if info_types[k] == "Flag":
+                body += bytes([0x00])
+            elif info_types[k] == "Integer":
+                body += _enc_ints([int(x) for x in v])
+            else:
+                body += _enc_str(",".join(str(x) for x in v).encode())
+        out.append(_struct.pack("<II", len(body), 0) + body)
+    _bgzf_write(path, b"".join(out))
+
+
+def _dec_typed(data: bytes, o: int):
+    """-> (values, new offset): list of ints / floats, bytes for char vectors, [] for MISSING (flags)."""
+    d = data[o]
+    o += 1
+    count, typ = d >> 4, d & 15
+    if count == 15:
+        (n,), o = _dec_typed(data, o)
+        count = n
+    if typ == 0:
+        return [], o
+    if typ == 7:
+        return data[o:o + count], o + count
+    if typ == 5:
+        return list(_struct.unpack_from(f"<{count}f", data, o)), o + 4 * count
+    fmt, size, missing = _BCF_INT[typ]
+    vals = [v for v in _struct.unpack_from(f"<{count}{fmt}", data, o) if v != missing and v != missing + 1]  # missing / end-of-vector
+    return vals, o + size * count
+
+
+def read_candidate_bcf(path: str, label_to_index: Dict[str, int]) -> List[CandidateRecord]:
+    """Site records of a BCF2 file as CandidateRecords; chromosomes are mapped by NAME to the caller's chromosome list
+    (bcf_chrom_index_map, :566)."""
+    with _gzip.open(path, "rb") as f:
+        data = f.read()
+    assert data[:5] == b"BCF\x02\x02", "not a BCF2 file"
+    (l_text,) = _struct.unpack_from("<I", data, 5)
+    text = data[9:9 + l_text].rstrip(b"\0").decode()
+    # dictionaries: strings of FILTER / INFO / FORMAT lines in order of first appearance, PASS first; IDX= wins when present
+    names: Dict[int, str] = {0: "PASS"}
+    seen = {"PASS": 0}
+    contigs: List[str] = []
+    types: Dict[str, str] = {}
+    for line in text.split("\n"):
+        m = _re.match(r"##(FILTER|INFO|FORMAT)=<(.*)>", line)
+        if m:
+            attrs = dict(_re.findall(r"(\w+)=(\"[^\"]*\"|[^,]*)", m.group(2)))
+            name = attrs["ID"]
+            if m.group(1) == "INFO":
+                types[name] = attrs.get("Type", "String")
+            if name not in seen:
+                idx = int(attrs["IDX"]) if "IDX" in attrs else len(seen)
+                seen[name] = idx
+                names[idx] = name
+            continue
+        m = _re.match(r"##contig=<(.*)>", line)
+        if m:
+            attrs = dict(_re.findall(r"(\w+)=(\"[^\"]*\"|[^,]*)", m.group(1)))
+            contigs.append(attrs["ID"])
+    recs: List[CandidateRecord] = []
+    o = 9 + l_text
+    while o < len(data):
+        l_shared, l_indiv = _struct.unpack_from("<II", data, o)
+        p = o + 8
+        chrom, pos, _rlen, _qual, n_allele_info, _n_fmt_sample = _struct.unpack_from("<iiifII", data, p)
+        p += 24
+        n_allele, n_info = n_allele_info >> 16, n_allele_info & 0xFFFF
+        rid, p = _dec_typed(data, p)
+        alleles = []
+        for _ in range(n_allele):
+            a, p = _dec_typed(data, p)
+            alleles.append(bytes(a))
+        _flt, p = _dec_typed(data, p)
+        info: Dict[str, List[Union[int, str]]] = {}
+        for _ in range(n_info):
+            (k,), p = _dec_typed(data, p)
+            v, p = _dec_typed(data, p)
+            key = names[k]
+            if isinstance(v, (bytes, bytearray)):
+                info[key] = [x for x in bytes(v).decode().split(",")] if v else []
+            else:
+                info[key] = list(v)
+        recs.append(CandidateRecord(label_to_index[contigs[chrom]], pos, bytes(rid).decode(), alleles, info))
+        o += 8 + l_shared + l_indiv
+    return recs

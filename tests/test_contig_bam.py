@@ -231,3 +231,96 @@ def test_candidate_records_to_refined_svs():
     assert (b.bp.insert_seq, b.bp.breakend1_neighbor, b.bp.breakend2_neighbor) == (b"CT", (7, 1), None)
     assert not b.bp.is_indel() and b.bp.deletion_size() is None
     assert CS.process_record_to_anno_refined_sv(l2i, recs[3]) is None
+
+
+def test_candidate_bcf_round_trip_and_layout(tmp_path):
+    """BCF2 subset used by candidate.sv.bcf: encoder / decoder round trip, typed-value layout per the VCF specification,
+    and the decoded records feed the same record -> breakpoint logic as the VCF text form."""
+    from sawfish_b200 import candidate_sv as CS
+    chroms = [("chr1", 248956422), ("chr20", 64444167)]
+    l2i = {"chr20": 0, "chr1": 1}          # the caller's chromosome order differs from the file's: mapped by name
+    types = {"SVTYPE": "String", "END": "Integer", "SVLEN": "Integer", "HOMLEN": "Integer", "HOMSEQ": "String", "INSSEQ": "String",
+             "CONTIG_POS": "Integer", "OVERLAP_ASM": "Integer", "BND0_NEIGHBOR": "String", "IMPRECISE": "Flag"}
+    file_index = {n: i for i, (n, _l) in enumerate(chroms)}
+    lines = [
+        "chr20\t1001\tsawfish:0:3:0:0\tA\t<DEL>\t.\t.\tSVTYPE=DEL;END=1501;SVLEN=500;HOMLEN=3;HOMSEQ=CAG;INSSEQ=TT;CONTIG_POS=1499",
+        "chr20\t2001\tsawfish:0:4:0:0\tG\tG" + "ACGT" * 40 + "\t.\t.\tSVTYPE=INS;END=2001;SVLEN=160;CONTIG_POS=70000;OVERLAP_ASM=0,1;IMPRECISE",
+        "chr1\t5001\tsawfish:0:5:0:0:0\tT\tTCT]chr20:9000]\t.\t.\tSVTYPE=BND;HOMLEN=2;HOMSEQ=AC;CONTIG_POS=1498;BND0_NEIGHBOR=7:1",
+    ]
+    recs_file_order = [CS.parse_vcf_record_line(x, file_index) for x in lines]
+    path = str(tmp_path / CS.CANDIDATE_SV_FILENAME)
+    CS.write_candidate_bcf(path, chroms, recs_file_order, types)
+    got = CS.read_candidate_bcf(path, l2i)
+    want = [CS.parse_vcf_record_line(x, l2i) for x in lines]
+    assert len(got) == 3
+    for g, w in zip(got, want):
+        assert (g.chrom_index, g.pos, g.id, g.alleles) == (w.chrom_index, w.pos, w.id, w.alleles)
+        assert {k: [str(x) for x in v] for k, v in g.info.items()} == {k: [str(x) for x in v] for k, v in w.info.items()}
+        a, b = CS.process_record_to_anno_refined_sv(l2i, g), CS.process_record_to_anno_refined_sv(l2i, w)
+        assert (a.bp, a.contig_map, a.contig_pos_before_breakend1) == (b.bp, b.contig_map, b.contig_pos_before_breakend1)
+    # layout spot checks on the uncompressed stream
+    import gzip
+    raw = gzip.open(path, "rb").read()
+    assert raw[:5] == b"BCF\x02\x02"
+    (l_text,) = struct.unpack_from("<I", raw, 5)
+    assert raw[9 + l_text - 1] == 0 and b"##contig=<ID=chr20" in raw[9:9 + l_text]
+    o = 9 + l_text
+    l_shared, l_indiv = struct.unpack_from("<II", raw, o)
+    chrom, pos, rlen, qual_bits, nai, nfs = struct.unpack_from("<iiiIII", raw, o + 8)
+    assert (l_indiv, chrom, pos, rlen, qual_bits, nai >> 16, nai & 0xFFFF, nfs) == (0, 1, 1000, 501, 0x7F800001, 2, 7, 0)
+    assert raw[o + 32] == 0xF7 and raw[o + 33] == 0x11 and raw[o + 34] == 15          # ID: 15 chars -> overflow count form
+    assert CS._enc_ints([1499]) == bytes([0x12]) + struct.pack("<h", 1499) and CS._enc_ints([70000])[0] == 0x13
+    assert CS._dec_typed(bytes([0x21, 5, 0x81]), 0) == ([5], 3)                         # end-of-vector padding is dropped
+
+
+def _write_discover_dirs(rng, tmp_path, n_samples):
+    """Per sample: contig.alignment.bam + candidate.sv.bcf for one insertion locus with a few true alleles."""
+    from sawfish_b200 import candidate_sv as CS
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    left, right = acgt[rng.integers(0, 4, 250)], acgt[rng.integers(0, 4, 250)]
+    alleles = [acgt[rng.integers(0, 4, int(rng.integers(40, 140)))] for _ in range(3)]
+    types = {"SVTYPE": "String", "END": "Integer", "SVLEN": "Integer", "CONTIG_POS": "Integer"}
+    dirs, truth = [], []
+    for s in range(n_samples):
+        picks = rng.choice(3, size=int(rng.integers(1, 3)), replace=False)
+        contigs, recs = [], []
+        for ai, a in enumerate(picks):
+            ins = alleles[int(a)]
+            seq = np.concatenate([left, ins, right])
+            for _e in range(int(rng.integers(0, 3))):
+                p = int(rng.integers(0, len(seq)))
+                seq[p] = acgt[int(rng.integers(0, 4))]
+            pos = 40_000 + int(rng.choice([0, 2, 40]))          # leftmost aligned base of the contig
+            segs = [CB.ContigAlignmentSegment(1, pos, [("=", 250), ("I", len(ins)), ("=", 250)])]
+            contigs.append(CB.ContigAlignmentInfo(s, 0, ai, seq.tobytes(), 0, segs, int(rng.integers(3, 30)),
+                                                  (int(rng.integers(0, 20)), len(seq) - int(rng.integers(0, 20)))))
+            anchor = pos + 249                                   # 0-based last reference base before the insertion
+            ref_base = chr(seq[249]).encode()
+            recs.append(CS.CandidateRecord(1, anchor, f"sawfish:{s}:0:{ai}:0", [ref_base, ref_base + seq[250:250 + len(ins)].tobytes()],
+                                           {"SVTYPE": ["INS"], "END": [anchor + 1], "SVLEN": [len(ins)], "CONTIG_POS": [249]}))
+            truth.append(int(a))
+        d = tmp_path / f"discover{s}"
+        d.mkdir()
+        CB.write_contig_alignments(str(d / CB.CONTIG_ALIGNMENT_FILENAME), CHROMS, contigs)
+        CS.write_candidate_bcf(str(d / CS.CANDIDATE_SV_FILENAME), CHROMS, recs, types)
+        dirs.append(str(d))
+    return dirs, truth
+
+
+def test_discover_dirs_to_merge_pools(tmp_path):
+    """Both files of the hand-off, per sample, through load_discover_dir into the duplicate-haplotype pooling."""
+    from sawfish_b200 import discover_dir as DD
+    rng = np.random.default_rng(12)
+    dirs, truth = _write_discover_dirs(rng, tmp_path, n_samples=5)
+    l2i = {n: i for i, (n, _l) in enumerate(CHROMS)}
+    samples = [DD.load_discover_dir(d, l2i) for d in dirs]
+    haps, sample_lists = DD.merge_haplotypes_of_samples(samples)
+    assert len(haps) == len(truth) and all(len(h.breakpoints) == 1 for h in haps)
+    assert all(h.breakpoints[0].deletion_size == 0 and h.breakpoints[0].insert_size >= 40 for h in haps)
+    merge = O.bio_scoring(0, -2, 1, -3, yclip_prefix=0, yclip_suffix=0)
+    pools, _ = MP.get_haplotype_merge_pools(haps, sample_lists, lambda pairs: [O.bio_custom_align(merge, q, b)[0] for b, q in pairs])
+    for p in pools:
+        assert len({truth[h] for h in p}) <= 1
+    assert sum(1 for p in pools if p) == len(set(truth))
+    with pytest.raises(FileNotFoundError):
+        DD.load_discover_dir(str(tmp_path / "missing"), l2i)
