@@ -22,9 +22,10 @@
 // band goes to a boundary array (8 bytes per column, L2 resident) that the warp doing the next band reads 32 columns
 // at a time, one batch ahead, as soon as a progress word in shared memory says they are there: the four warps work on
 // four consecutive bands at once, each 64 columns behind the previous one (band b reads buffer b % 5, writes buffer
-// (b + 1) % 5; the warp that last read a buffer is the one that overwrites it, so producers never wait).  10 integer instructions per matrix cell: 6 on the alu pipe
-// (4 x VIADDMNMX, 2 x VIMNMX), 4 on the fma pipe (the substitution score as dg + ma - min((x - y)^2, 1) * (ma - mi)); bound by
-// the alu pipe (ncu: 86.6 % busy in the 7-alu-instruction version).  No tensor cores (integer DP).
+// (b + 1) % 5; the warp that last read a buffer is the one that overwrites it, so producers never wait).
+// 10 integer instructions per matrix cell: 6 on the alu pipe (4 x VIADDMNMX, 2 x VIMNMX), 4 on the fma pipe (the
+// substitution score as dg + ma - min((x - y)^2, 1) * (ma - mi)); bound by the alu pipe (ncu: 86.6 % busy in the
+// 7-alu-instruction version).  No tensor cores (integer DP).
 #pragma once
 #include "sfc_k_bio.cuh"
 
@@ -48,8 +49,9 @@ constexpr int K5_WARPS = 4, K5_NBUF = K5_WARPS + 1, K5_TAG_SHIFT = 20;  // progr
 
 struct K5Batch { int s, i, y; };
 
-// Boundary rows are written by lane 31 of the same warp one band earlier: read them through L2 (never the
-// non-coherent path), ordered by the __syncwarp() between bands.
+// Boundary rows are written by lane 31 of ANOTHER warp of the CTA (the one doing the previous band, 64+ columns ahead):
+// wait on that band's progress word, then read through L2 (never the non-coherent path; the producer's fence + progress
+// store and the fence here order the data).
 __device__ __forceinline__ K5Batch k5_load(const int2* in, const volatile int* prog_in, int in_tag,
                                            const uint8_t* __restrict__ y, int n, int base, int lane) {
   K5Batch b{K4_MIN_SCORE, K4_MIN_SCORE, 0};
