@@ -216,3 +216,67 @@ def test_split_read_segment_matches_its_breakend():
     assert not RF.does_read_segment_match_breakend(False, be1, be2, info3)
     assert RF.get_split_read_info(l2i, 0, 4000, False, cg("2000M"), 60, None, False) is None       # not split: no check
     assert RF.get_split_read_info(l2i, 0, 4000, False, cg("1000M1000S"), 60, "chr1,9001,+,1000S1000M,60,0;", True) is None
+
+
+def test_cigar_walkers_against_per_base_maps():
+    """Independent check of the cigar walkers: expand random alignments into explicit read<->ref base maps and compare."""
+    rng = np.random.default_rng(77)
+    for _ in range(300):
+        cigar, ref_pos0 = [], int(rng.integers(0, 50))
+        if rng.random() < 0.4:
+            cigar.append(("S", int(rng.integers(1, 8))))
+        n_blocks = int(rng.integers(1, 5))
+        for b in range(n_blocks):
+            cigar.append((str(rng.choice(["M", "=", "X"])), int(rng.integers(3, 12))))
+            if b + 1 < n_blocks:
+                cigar.append((str(rng.choice(["I", "D"])), int(rng.integers(1, 6))))
+        if rng.random() < 0.4:
+            cigar.append(("S", int(rng.integers(1, 8))))
+        # per-base map of aligned (read_pos, ref_pos)
+        aligned, read_pos, ref_pos = [], 0, ref_pos0
+        for op, n in cigar:
+            if op in "M=X":
+                aligned += [(read_pos + i, ref_pos + i) for i in range(n)]
+            read_pos += n if op in "MIS=X" else 0
+            ref_pos += n if op in "MDN=X" else 0
+        ref_to_read = {r: q for q, r in aligned}
+        lo, hi = aligned[0][1], aligned[-1][1]
+        for target in range(lo - 3, hi + 4):
+            got = RF.get_alignment_closest_to_target_ref_pos(ref_pos0, cigar, target, RF.ANY)
+            if target in ref_to_read:                                   # an aligned base: exact answer in every mode
+                assert got == (ref_to_read[target], target)
+                assert RF.get_alignment_closest_to_target_ref_pos(ref_pos0, cigar, target, RF.TARGET) == got
+            else:
+                assert got is not None
+                best = min(abs(r - target) for _q, r in aligned)
+                assert abs(got[1] - target) == best and ref_to_read[got[1]] == got[0]
+                lower = RF.get_alignment_closest_to_target_ref_pos(ref_pos0, cigar, target, RF.TARGET_OR_LOWER)
+                higher = RF.get_alignment_closest_to_target_ref_pos(ref_pos0, cigar, target, RF.TARGET_OR_HIGHER)
+                assert lower is None or lower[1] < target
+                assert higher is None or higher[1] > target
+        # a ref range whose two ends are aligned bases maps to exactly their read positions
+        a, b = sorted(int(x) for x in rng.choice(len(aligned), 2, replace=False))
+        rng_ref = (aligned[a][1], aligned[b][1])
+        assert RF.translate_ref_range_to_hardclipped_read_range(ref_pos0, cigar, rng_ref) == (aligned[a][0], aligned[b][0])
+        # gap-compressed identity: =/X counted as written, M compared base by base, one event per indel
+        ref_seq = bytes(rng.choice(list(b"ACGT"), ref_pos + 5).tolist())
+        read = bytearray(rng.choice(list(b"ACGT"), read_pos).tolist())
+        match = mism = 0
+        q, r = 0, ref_pos0
+        for op, n in cigar:
+            if op == "=":
+                match += n
+            elif op == "X":
+                mism += n
+            elif op == "M":
+                for i in range(n):
+                    if read[q + i] == ref_seq[r + i]:
+                        match += 1
+                    else:
+                        mism += 1
+            elif op in "ID":
+                mism += 1
+            q += n if op in "MIS=X" else 0
+            r += n if op in "MDN=X" else 0
+        want = 1.0 if match + mism == 0 else match / (match + mism)
+        assert RF.get_gap_compressed_identity_from_alignment(ref_pos0, cigar, bytes(read), ref_seq, True) == want
