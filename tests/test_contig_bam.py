@@ -324,3 +324,39 @@ def test_discover_dirs_to_merge_pools(tmp_path):
     assert sum(1 for p in pools if p) == len(set(truth))
     with pytest.raises(FileNotFoundError):
         DD.load_discover_dir(str(tmp_path / "missing"), l2i)
+
+
+def test_refined_svs_to_sv_groups_index_remapping():
+    """process_rsv_cluster_to_sv_group / group_single_sample_refined_svs (get_refined_svs.rs:606-846)."""
+    from sawfish_b200 import candidate_sv as CS
+    from sawfish_b200 import discover_dir as DD
+
+    def asm(tag):
+        return CB.ClusterAssembly([], tag)               # supporting_read_count doubles as a label here
+
+    def sv(cluster, assembly, alignment, contig_map):
+        be = CS.RecBreakend(0, 100, 101, CS.LEFT_ANCHOR)
+        return CS.AnnotatedRefinedSV(CS.SVUniqueIdData(0, cluster, assembly, alignment), CS.RecBreakpoint(be, be, b""), b"", 0, contig_map)
+
+    contigs = [[asm(10), asm(11), asm(12)], [asm(20)], [asm(30), asm(31)]]
+    svs = [sv(2, 1, 0, [0, 1]), sv(0, 2, 0, [2, 0]), sv(0, 0, 1, [2, 0]), sv(0, 0, 0, [2, 0]), sv(0, 1, 0, [2, 0]), sv(1, 0, 0, [0]),
+           sv(2, 0, 0, [0, 1])]
+    groups = DD.group_single_sample_refined_svs(contigs, svs)
+    assert [g.cluster_index for g in groups] == [0, 1, 2]
+    g0 = groups[0]
+    # cluster 0: the sample's haplotypes are assemblies [2, 0] (first SV in sorted order is (0,0,0) with contig map [2, 0]);
+    # assembly 1 is dropped with its SV, the others are re-indexed in contig-map order: 2 -> 0, 0 -> 1
+    # (the reference keeps the surviving haplotypes in their ORIGINAL order while numbering them in contig-map order, :712-733;
+    #  the two agree because discover writes ascending contig maps — the descending map here pins the mirrored behaviour)
+    assert [h.supporting_read_count for h in g0.group_haplotypes] == [10, 12]      # kept in original order
+    assert g0.sample_haplotype_list == [[0, 1]]
+    assert [(s.id.assembly_index, s.id.alignment_index) for s in g0.refined_svs] == [(0, 0), (0, 1), (2, 0)]
+    assert g0.sv_haplotype_map == [1, 1, 0]
+    assert groups[1].sample_haplotype_list == [[0]] and groups[1].sv_haplotype_map == [0]
+    assert groups[2].sample_haplotype_list == [[0, 1]] and groups[2].sv_haplotype_map == [0, 1]
+    # haploid / multi-region loci keep one haplotype: the SV on the other assembly goes away with it
+    g2 = DD.group_single_sample_refined_svs(contigs, svs, lambda c: 1)[2]
+    assert len(g2.group_haplotypes) == 1 and [s.id.assembly_index for s in g2.refined_svs] == [0] and g2.sv_haplotype_map == [0]
+    # a cluster whose only SVs sit on dropped haplotypes yields no group
+    only = [sv(0, 1, 0, [2])]
+    assert DD.group_single_sample_refined_svs(contigs, only, lambda c: 1) == []
