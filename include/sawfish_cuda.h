@@ -40,12 +40,20 @@ typedef enum {
   SFC_ERR_CUDA = -3,        /* CUDA runtime error; see sfc_last_error */
   SFC_ERR_CAPACITY = -4,    /* caller's output buffer too small */
   SFC_ERR_UNSUPPORTED = -5, /* symbol outside {A,C,G,T,N,a,c,g,t,n}, or sequence too long for shared memory */
-  SFC_ERR_OOM = -6          /* device workspace exhausted even with one pair in flight */
+  SFC_ERR_OOM = -6,         /* device workspace exhausted even with one pair in flight */
+  SFC_ERR_INTERNAL = -9     /* a per-pair SFC_STATUS_INTERNAL / SFC_STATUS_POOL / SFC_STATUS_MAX_SCORE surfaced through the per-pair API */
 } sfc_error;
 
 /* Per-pair status, mirrors rust_wfa2::aligner::AlignmentStatus so the caller can keep its
  * assert_eq!(status, StatusAlgCompleted) (src/wfa2_utils.rs:117). */
-enum { SFC_STATUS_COMPLETED = 0, SFC_STATUS_UNSUPPORTED = -5, SFC_STATUS_OOM = -6, SFC_STATUS_MAX_SCORE = -7 };
+enum {
+  SFC_STATUS_COMPLETED = 0,
+  SFC_STATUS_UNSUPPORTED = -5, /* sequences do not fit the kernel's shared-memory windows */
+  SFC_STATUS_OOM = -6,         /* device workspace too small even with one pair in flight */
+  SFC_STATUS_MAX_SCORE = -7,   /* score cap reached */
+  SFC_STATUS_INTERNAL = -9,    /* backtrace inconsistency (a bug: never expected) */
+  SFC_STATUS_POOL = -10        /* run-length ops pool short; only seen transiently (the library grows the pool and re-runs) */
+};
 
 /* metric 0 = gap-linear (indel penalty = gap_ext1; gap_open1 ignored)   WFAlignerGapLinear::new_with_match
  * metric 1 = gap-affine 2-piece                                          WFAlignerGapAffine2Pieces::new_with_match
@@ -103,7 +111,11 @@ int sfc_align_batch(sfc_ctx*, const sfc_penalties*, const uint8_t* seq_arena, si
                     uint32_t* ops_rle, size_t ops_cap, uint64_t* ops_off);
 
 /* Staged form of the same call (what a pipelined submitter thread uses; also how bench.py separates
- * device-resident throughput from end-to-end throughput). */
+ * device-resident throughput from end-to-end throughput).
+ * Buffer lifetime: seq_arena and pairs are only read inside sfc_batch_upload — when it returns (OK or error) the
+ * copy of the arena to the device has completed and the pair table has been copied to library-owned memory, so
+ * the caller may refill or free both immediately (a pinned arena overlaps its copy with the validation of the
+ * pair table inside the call).  The output buffers of sfc_batch_download are written before it returns. */
 int sfc_batch_upload(sfc_ctx*, const uint8_t* seq_arena, size_t arena_len, const sfc_pair* pairs, size_t n_pairs);
 int sfc_batch_run(sfc_ctx*, const sfc_penalties*, int want_cigar);
 int sfc_batch_download(sfc_ctx*, int32_t* scores, int32_t* status,

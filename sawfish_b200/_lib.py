@@ -15,7 +15,7 @@ CSRC = os.path.join(_PKG, "csrc")
 
 SFC_OK = 0
 ERRORS = {-1: "SFC_ERR_INVALID", -2: "SFC_ERR_NO_DEVICE", -3: "SFC_ERR_CUDA", -4: "SFC_ERR_CAPACITY",
-          -5: "SFC_ERR_UNSUPPORTED", -6: "SFC_ERR_OOM"}
+          -5: "SFC_ERR_UNSUPPORTED", -6: "SFC_ERR_OOM", -9: "SFC_ERR_INTERNAL"}
 
 
 class SfcError(RuntimeError):

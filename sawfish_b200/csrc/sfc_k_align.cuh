@@ -1052,7 +1052,7 @@ __global__ void __launch_bounds__(K2_LB_T, K2_LB_B) k2_align(const K2Params P) {
             if (lane == 0) base = atomicAdd(P.pool_used, (unsigned long long)nf);
             base = __shfl_sync(FULL, base, 0);
             __syncwarp();
-            if (base + (unsigned long long)nf > P.pool_cap) { res_status = -4; }
+            if (base + (unsigned long long)nf > P.pool_cap) { res_status = -10; /* SFC_STATUS_POOL */ }
             else {
               for (int i = lane; i < nf; i += 32) P.pool[base + i] = tmp_f[i];
               o_off = base; o_len = (uint32_t)nf;

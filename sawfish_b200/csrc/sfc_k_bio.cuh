@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256) k4_bio_align(const K4Params P) {
       uint32_t olen = 0;
       if (!bad) {
         base = atomicAdd(P.pool_used, (unsigned long long)cnt);
-        if (base + (unsigned long long)cnt > P.pool_cap) st = -4;
+        if (base + (unsigned long long)cnt > P.pool_cap) st = -10;  // SFC_STATUS_POOL (cannot happen: the host sizes the pool for every op)
         else {
           for (int a = 0; a < cnt; ++a) P.pool[base + a] = tmp[cnt - 1 - a];  // alignment order
           olen = (uint32_t)cnt;

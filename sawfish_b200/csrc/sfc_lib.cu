@@ -143,6 +143,9 @@ int adjust_penalties(const sfc_penalties* pen, AdjPen* a) {
   return 0;
 }
 
+// [off, off + len) inside [0, arena_len) without wrapping in uint64
+inline bool in_arena(uint64_t off, uint64_t len, uint64_t arena_len) { return off <= arena_len && len <= arena_len - off; }
+
 long long gap_cost(const AdjPen& a, long long L) {
   if (L <= 0) return 0;
   if (a.metric == 0) return (long long)a.e1 * L;
@@ -275,6 +278,7 @@ extern "C" int sfc_batch_upload(sfc_ctx* c, const uint8_t* arena, size_t arena_l
   if ((rc = ensure(c, c->d_arena, arena_len))) return rc;
   CU(cudaEventRecord(c->ev[0], c->stream));
   CU(cudaMemcpyAsync(c->d_arena.p, arena, arena_len, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaEventRecord(c->ev[7], c->stream));  // waited for before this call returns: the caller may then reuse `arena`
   // an argument error below must not return while that copy still reads the caller's buffer
   auto bad = [&](const char* fmt, size_t i) { cudaStreamSynchronize(c->stream); return fail(c, SFC_ERR_INVALID, fmt, i); };
   uint64_t woff = 0;
@@ -282,7 +286,7 @@ extern "C" int sfc_batch_upload(sfc_ctx* c, const uint8_t* arena, size_t arena_l
     const sfc_pair& p = pairs[i];
     if (p.pattern_len == 0 || p.text_len == 0) return bad("pair %zu: empty sequence", i);
     if (p.pattern_len > 0x3FFFFFFFu || p.text_len > 0x3FFFFFFFu) return bad("pair %zu: sequence too long", i);
-    if (p.pattern_off + p.pattern_len > arena_len || p.text_off + p.text_len > arena_len)
+    if (!in_arena(p.pattern_off, p.pattern_len, arena_len) || !in_arena(p.text_off, p.text_len, arena_len))
       return bad("pair %zu: sequence outside arena", i);
     if (p.pattern_begin_free < 0 || p.pattern_end_free < 0 || p.text_begin_free < 0 || p.text_end_free < 0 ||
         (uint32_t)p.pattern_begin_free > p.pattern_len || (uint32_t)p.pattern_end_free > p.pattern_len ||
@@ -322,6 +326,8 @@ extern "C" int sfc_batch_upload(sfc_ctx* c, const uint8_t* arena, size_t arena_l
   c->stats = sfc_batch_stats{};
   c->stats.h2d_bytes = arena_len + 2 * n * sizeof(SeqDesc) + (2 * n + 1) * 4 + n * sizeof(DevPair);
   c->stats.launches = 1;
+  // the caller's arena has been read completely (include/sawfish_cuda.h: buffer lifetime); the pack kernel keeps running
+  CU(cudaEventSynchronize(c->ev[7]));
   c->uploaded = true;
   return SFC_OK;
 }
@@ -652,7 +658,8 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     std::vector<uint32_t> retry, cur(c->h_order.begin() + k2s_begin, c->h_order.end());
     int divisor = 1;
     const int force_c_env = getenv("SFC_K2_CLUSTER") ? atoi(getenv("SFC_K2_CLUSTER")) : 0;
-    for (int pass = 0; pass < 12; ++pass) {
+    // (a pass that only grows the ops pool does not count against the 12 workspace escalations: it always makes progress)
+    for (int pass = 0, pool_passes = 0; pass < 12 && pool_passes < 64; ++pass) {
       c->h_status.resize(n);
       CU(cudaMemcpyAsync(c->h_status.data(), c->d_status.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
       CU(cudaStreamSynchronize(c->stream));
@@ -661,7 +668,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       for (uint32_t pi : cur) {
         const int stt = c->h_status[pi];
         if (stt == SFC_STATUS_OOM) retry.push_back(pi);
-        else if (stt == -4) { retry.push_back(pi); pool_short = true; }
+        else if (stt == SFC_STATUS_POOL) { retry.push_back(pi); pool_short = true; }
       }
       if (retry.empty()) break;
       if (divisor >= (1 << 20)) break;  // nothing left to escalate: statuses stay -6
@@ -678,7 +685,10 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
         c->d_pool = bigger;
         pool_cap = c->d_pool.cap / 4;
       }
-      divisor *= 4;
+      bool oom_any = false;
+      for (uint32_t pi : retry) oom_any = oom_any || c->h_status[pi] == SFC_STATUS_OOM;
+      if (oom_any) divisor *= 4;
+      else { --pass; ++pool_passes; }  // pool growth only: same slabs, bigger pool
       Plan pl;
       // the pairs that ran out of choice bytes are the heaviest ones: when few are left, spread each over a cluster
       int Cr = 1;
@@ -935,7 +945,8 @@ extern "C" int sfc_aligner_align(sfc_aligner* a, const uint8_t* pattern, size_t 
   uint64_t off[2] = {0, 0};
   int rc = sfc_align_batch(c, &a->pen, arena.data(), arena.size(), &pr, 1, 1, score, &status, ops.data(), ops.size(), off);
   if (rc) return rc;
-  if (status != 0) return fail(c, status, "align: pair status %d", status);
+  if (status != 0)  // per-pair status -> sfc_error: only -5 / -6 share their meaning with the error enum
+    return fail(c, (status == SFC_STATUS_UNSUPPORTED || status == SFC_STATUS_OOM) ? status : SFC_ERR_INTERNAL, "align: pair status %d", status);
   int hm = 0;
   size_t nc = 0;
   int64_t roff = 0;
@@ -1072,7 +1083,7 @@ extern "C" int sfc_multi_align_batch(sfc_multi* m, const sfc_penalties* pen, con
         const size_t b = n * t / T, e = n * (t + 1) / T;
         trc[t] = sfc_estimate_pair_work(pen, pairs + b, e - b, work.data() + b);
         for (size_t i = b; i < e && !trc[t]; ++i)
-          if (pairs[i].pattern_off + pairs[i].pattern_len > arena_len || pairs[i].text_off + pairs[i].text_len > arena_len) trc[t] = -100;
+          if (!in_arena(pairs[i].pattern_off, pairs[i].pattern_len, arena_len) || !in_arena(pairs[i].text_off, pairs[i].text_len, arena_len)) trc[t] = -100;
       });
     }
     for (auto& t : pt) t.join();
@@ -1230,7 +1241,7 @@ extern "C" int sfc_bio_align_batch(sfc_ctx* c, const sfc_bio_scoring* sco, const
   for (size_t i = 0; i < n; ++i) {
     const sfc_pair& p = pairs[i];
     if (p.pattern_len == 0 || p.text_len == 0) return fail(c, SFC_ERR_INVALID, "pair %zu: empty sequence", i);  // assert!(!text.is_empty())
-    if (p.pattern_off + p.pattern_len > arena_len || p.text_off + p.text_len > arena_len)
+    if (!in_arena(p.pattern_off, p.pattern_len, arena_len) || !in_arena(p.text_off, p.text_len, arena_len))
       return fail(c, SFC_ERR_INVALID, "pair %zu outside the arena", i);
     if (p.pattern_len > 1000000u || p.text_len > 1000000u) return fail(c, SFC_ERR_UNSUPPORTED, "pair %zu: sequence too long", i);
     hp[i] = K4Pair{p.pattern_off, p.text_off, (int)p.pattern_len, (int)p.text_len};
@@ -1290,11 +1301,18 @@ extern "C" int sfc_bio_align_batch(sfc_ctx* c, const sfc_bio_scoring* sco, const
     size_t total = 0;
     for (size_t i = 0; i < n; ++i) total += (status[i] == 0) ? h_len[i] : 0;
     if (total > ops_cap) return fail(c, SFC_ERR_CAPACITY, "ops_cap %zu < %zu words", ops_cap, total);
+    // one copy of the used part of the pool, scattered into pair order on the host
+    unsigned long long used = 0;
+    CU(cudaMemcpy(&used, d_tail, 8, cudaMemcpyDeviceToHost));
+    const size_t valid = std::min<size_t>((size_t)used, pool_cap);
+    c->h_pool.resize(valid);
+    if (valid) CU(cudaMemcpy(c->h_pool.data(), c->d_b_pool.p, valid * 4, cudaMemcpyDeviceToHost));
     size_t pos = 0;
     for (size_t i = 0; i < n; ++i) {
       ops_off[i] = pos;
       if (status[i] == 0 && h_len[i]) {
-        CU(cudaMemcpyAsync(ops + pos, (uint32_t*)c->d_b_pool.p + h_off[i], (size_t)h_len[i] * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (h_off[i] + h_len[i] > valid) return fail(c, SFC_ERR_INTERNAL, "pair %zu: ops outside the pool", i);
+        memcpy(ops + pos, c->h_pool.data() + h_off[i], (size_t)h_len[i] * 4);
         pos += h_len[i];
       }
     }
@@ -1323,7 +1341,7 @@ extern "C" int sfc_bio_score_batch(sfc_ctx* c, const sfc_bio_scoring* sco, const
   for (size_t i = 0; i < n; ++i) {
     const sfc_pair& p = pairs[i];
     if (p.pattern_len == 0 || p.text_len == 0) return fail(c, SFC_ERR_INVALID, "pair %zu: empty sequence", i);  // assert!(!text.is_empty())
-    if (p.pattern_off + p.pattern_len > arena_len || p.text_off + p.text_len > arena_len)
+    if (!in_arena(p.pattern_off, p.pattern_len, arena_len) || !in_arena(p.text_off, p.text_len, arena_len))
       return fail(c, SFC_ERR_INVALID, "pair %zu outside the arena", i);
     if (p.pattern_len > 1000000u || p.text_len > 1000000u) return fail(c, SFC_ERR_UNSUPPORTED, "pair %zu: sequence too long", i);
     hp[i] = K4Pair{p.pattern_off, p.text_off, (int)p.pattern_len, (int)p.text_len};

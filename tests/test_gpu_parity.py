@@ -205,3 +205,56 @@ def test_ops_pool_growth_path(ctx, oracle):
     arena, pairs = np.concatenate(chunks), np.array(rows, dtype=PAIR_DTYPE)
     compare_with_oracle(oracle, ctx, aff, arena, pairs, want_cigar=True)
     assert ctx.stats()["retries"] >= 1
+
+
+@pytest.mark.parametrize("preset", ["large_indel_cigar", "consensus_score", "consensus_cigar"])
+def test_config2_at_bench_size(ctx, oracle, preset):
+    """The configuration bench.py times (BASELINE configs[1]: 2-20 kb reads x 2 haplotypes, SV up to 5 kb) against the
+    oracle at full size: scores and run-length ops bit-exact (reference src/wfa2_utils.rs:209-219)."""
+    from sawfish_b200 import synth
+    lin, aff = _pens()
+    arena, pairs, _ = synth.config2_read_vs_haplotypes(64, seed=0x5AF15 + 2, len_lo=2000, len_hi=20000, sv_lo=35, sv_hi=5000)
+    assert int(pairs["text_len"].max()) > 15000
+    pen, wc = {"large_indel_cigar": (aff, True), "consensus_score": (lin, False), "consensus_cigar": (lin, True)}[preset]
+    compare_with_oracle(oracle, ctx, pen, arena, pairs, want_cigar=wc)
+    assert ctx.stats()["retries"] == 0
+
+
+def test_config2_bench_size_int16_rings(ctx, oracle, monkeypatch):
+    from sawfish_b200 import synth
+    _, aff = _pens()
+    monkeypatch.setenv("SFC_K2_NARROW", "1")
+    arena, pairs, _ = synth.config2_read_vs_haplotypes(48, seed=4242, len_lo=2000, len_hi=20000, sv_lo=35, sv_hi=5000)
+    compare_with_oracle(oracle, ctx, aff, arena, pairs, want_cigar=True)
+
+
+def test_config5_stress_at_size(ctx, oracle):
+    """BASELINE configs[4]: 10 kb+ insertion / duplication haplotypes at 1-5 % divergence, full CIGAR parity at a size
+    where the wavefronts are tens of thousands of diagonals wide and thousands of scores deep."""
+    from sawfish_b200 import synth
+    _, aff = _pens()
+    arena, pairs = synth.config5_stress(3, seed=0x5AF15 + 5, len_lo=10000, len_hi=16000)
+    assert int(pairs["pattern_len"].min()) >= 10000
+    compare_with_oracle(oracle, ctx, aff, arena, pairs, want_cigar=True)
+
+
+def test_arena_may_be_reused_as_soon_as_upload_returns(ctx, oracle):
+    """include/sawfish_cuda.h, buffer lifetime: sfc_batch_upload has finished reading the caller's (pinned) arena and pair
+    table when it returns, so a pipelined submitter may refill both right away."""
+    import torch
+    from sawfish_b200 import synth
+    lin, _ = _pens()
+    arena, pairs, _ = synth.config2b_score_sv_flanks(20000, seed=31)
+    want, st, _, _ = ctx.align_batch(lin, arena, pairs, False)
+    assert (st == 0).all()
+    a_pin = torch.from_numpy(arena.copy()).pin_memory()
+    p_pin = torch.from_numpy(pairs.view(np.uint8).copy()).pin_memory()
+    for _ in range(3):
+        a_pin.numpy()[:] = arena
+        p_pin.numpy()[:] = pairs.view(np.uint8)
+        ctx.upload_ptr(a_pin.data_ptr(), a_pin.numel(), p_pin.data_ptr(), len(pairs))
+        a_pin.numpy()[:] = ord("N")      # overwrite immediately: the library must not read these buffers any more
+        p_pin.numpy()[:] = 0
+        ctx.run(lin, False)
+        got, st, _, _ = ctx.download()
+        assert (st == 0).all() and (got == want).all()

@@ -24,7 +24,7 @@ workload = sys.argv[1] if len(sys.argv) > 1 else "config2b"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 cfg = bench.WORKLOADS[workload]
 pen = CONSENSUS_PENALTIES if cfg["preset"] == "consensus" else LARGE_INDEL_PENALTIES
-arena, pairs = bench.make_batch(workload, bench.DEFAULT_READS[workload], 0x5AF15 + 2)
+arena, pairs, _groups = bench.make_batch(workload, bench.DEFAULT_READS[workload], 0x5AF15 + 2)
 n = len(pairs)
 arena_pin = torch.from_numpy(arena).pin_memory()
 pairs_pin = torch.from_numpy(pairs.view(np.uint8)).pin_memory()
