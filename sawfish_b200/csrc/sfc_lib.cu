@@ -20,6 +20,7 @@
 
 #include "sfc_device.cuh"
 #include "sfc_k_align.cuh"
+#include "sfc_k_align2.cuh"
 #include "sfc_k_bio.cuh"
 #include "sfc_k_bio_score.cuh"
 #include "sfc_k_pack.cuh"
@@ -511,7 +512,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     }
 
     // size one job's launch: returns grid (in clusters), slab bytes, shared bytes, win_cap
-    struct Plan { size_t n_cl, slab, smem, max_fixed; int win_cap, stages; bool wide; };
+    struct Plan { size_t n_cl, slab, smem, max_fixed; int win_cap, stages; bool wide; bool v2; };
     // max_est: estimated wavefront cells of the heaviest pair of the list (0 = unknown).  One choice byte is kept per cell,
     // so the slab's choice-byte budget follows it: a pair that runs out is re-run from scratch in an escalation pass, at
     // the tail of the batch, which costs far more than the memory does (180 GB of HBM).
@@ -533,6 +534,54 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
         max_fixed = std::max(max_fixed, fixed);
         max_win = std::max(max_win, (size_t)(d.plen >> 3) + (d.tlen >> 3) + 2);
         max_W = std::max(max_W, Wp);
+      }
+      // ---- K2 v2 (sfc_k_align2.cuh): affine 2-piece, texts up to 64 000 bases, wavefront history kept (10 B per cell) ----
+      pl->v2 = false;
+      if (a.metric == 1 && !getenv("SFC_K2_V1")) {
+        bool fits = true;
+        size_t v2_fixed = 0;
+        for (uint32_t pi : list) {
+          const DevPair& d = c->h_pairs[pi];
+          fits = fits && d.tlen <= V2_MAX_TLEN;
+          long long scap = gap_cost(a, d.plen) + gap_cost(a, d.tlen) + 1;
+          scap = std::min<long long>(scap, INT_MAX / 4);
+          v2_fixed = std::max(v2_fixed, ((size_t)scap + 1) * V2_HIST * 4 + 2 * (((size_t)d.plen + d.tlen + 8) * 4) + 256);
+        }
+        const size_t nslots2 = ((size_t)nslots + 1) & ~(size_t)1;
+        const size_t fixed_sm2 = (max_win * 8 + nslots2 * 20 + V2_MISC_BYTES + 15) & ~(size_t)15;
+        const size_t per_stage2 = (size_t)(threads / 32) * 7 * V2_ROWB;
+        int st2 = 2;
+        if (const char* e = getenv("SFC_K2_STAGES")) st2 = std::max(1, std::min(3, atoi(e)));
+        while (st2 > 1 && fixed_sm2 + st2 * per_stage2 > c->smem_optin) --st2;
+        if (fits && fixed_sm2 + st2 * per_stage2 <= c->smem_optin) {
+          pl->v2 = true;
+          pl->wide = false;
+          pl->win_cap = (int)max_win;
+          pl->stages = st2;
+          pl->smem = fixed_sm2 + st2 * per_stage2;
+          pl->max_fixed = v2_fixed;
+          CU(cudaFuncSetAttribute(k2v2_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+          int occ = 1;
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2v2_align, threads, pl->smem));
+          occ = std::max(1, occ);
+          size_t slots = (size_t)c->sm_count * occ / C;
+          if (C > 1) slots = std::max<size_t>(1, slots * 7 / 8);
+          const size_t n_cl = std::max<size_t>(1, std::min<size_t>(list.size(), slots) / divisor);
+          // rows: 10 B per wavefront cell.  The budget follows the work estimate of the heaviest pair (1.5 x); when the
+          // job's share of device memory cannot hold that for every resident pair the slabs shrink (never the number of
+          // resident pairs) and a pair that runs out is re-run in an escalation pass with a larger share.
+          size_t rows_want = std::max<size_t>((size_t)2048 * max_W * 10 * divisor, (size_t)16 << 20);
+          if (max_est > 0) rows_want = std::max<size_t>(rows_want, (size_t)(15.0 * max_est) + ((size_t)4 << 20));
+          rows_want = std::min<size_t>(rows_want, (size_t)64 << 30);
+          size_t slab = v2_fixed + rows_want;
+          size_t ncl = n_cl;
+          if (slab * ncl > budget) slab = budget / ncl;
+          while (ncl > 1 && slab < v2_fixed + ((size_t)8 << 20)) { ncl = (ncl + 1) / 2; slab = std::min(v2_fixed + rows_want, budget / ncl); }
+          if (slab < v2_fixed + 4096) return fail(c, SFC_ERR_OOM, "device workspace too small: need %zu B for one pair", v2_fixed);
+          pl->slab = slab & ~(size_t)255;
+          pl->n_cl = ncl;
+          return 0;
+        }
       }
       const size_t base = std::min(max_win * 8 + (size_t)nslots * 8 + K2_MISC_BYTES, c->smem_optin);
       pl->win_cap = (int)((base - (size_t)nslots * 8 - K2_MISC_BYTES) / 8);
@@ -601,7 +650,9 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      if (a.metric == 1) {
+      if (pl.v2) {
+        CU(cudaLaunchKernelEx(&cfg, k2v2_align, P));
+      } else if (a.metric == 1) {
         if (pl.wide) CU(cudaLaunchKernelEx(&cfg, k2_align<true, int32_t>, P)); else CU(cudaLaunchKernelEx(&cfg, k2_align<true, int16_t>, P));
       } else {
         if (pl.wide) CU(cudaLaunchKernelEx(&cfg, k2_align<false, int32_t>, P)); else CU(cudaLaunchKernelEx(&cfg, k2_align<false, int16_t>, P));

@@ -28,3 +28,17 @@ def test_cpp_host_side_vectors():
 def test_cpp_reference_unit_tests_on_gpu():
     r = subprocess.run([_build(), "gpu"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_k2v2_packed_recurrence_on_host():
+    """The s16x2 recurrence of the K2 v2 kernel (v2_recur8: funnel-shifted neighbours, saturating insertion increment, all
+    three chunk variants) against the scalar recurrence, on the CPU (the DPX intrinsics are emulated by the header)."""
+    exe = os.path.join(ROOT, "build", "test_v2_recur")
+    src = os.path.join(ROOT, "tests", "cpp", "test_v2_recur.cu")
+    hdr = os.path.join(ROOT, "sawfish_b200", "csrc", "sfc_k_align2.cuh")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe, src],
+                       check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
