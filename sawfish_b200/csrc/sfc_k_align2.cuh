@@ -175,10 +175,10 @@ __device__ __forceinline__ void v2_stage_guarded(unsigned char* stg, const int4*
   }
 }
 
-#ifndef V2_LB_T
-#define V2_LB_T 384
-#endif
-__global__ void __launch_bounds__(V2_LB_T, 1) k2v2_align(const K2Params P) {
+// Launch shapes: (threads per CTA, CTAs per SM).  One 384- or 512-thread CTA per SM, or two 256-thread CTAs (two pairs
+// per SM: one pair's serial trim / plan section overlaps the other's cell phase).
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
   extern __shared__ __align__(16) unsigned char k2_smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int C = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
@@ -373,7 +373,6 @@ __global__ void __launch_bounds__(V2_LB_T, 1) k2v2_align(const K2Params P) {
       int4* outU = reinterpret_cast<int4*>(slab + fixed);
       int term_k = INT_MAX;
 
-      auto in_rng = [&](int k, int row) -> bool { return (unsigned)(k - misc[V2_RLO + row]) < (unsigned)misc[V2_RCNT + row]; };
       auto kind_of = [&](int gb) -> int {
         if (gb >= G1A && gb <= G1B) return 1;
         if (gb >= G2A && gb <= G2B && (gb <= M2A || gb >= M2B)) return 2;
@@ -434,31 +433,51 @@ __global__ void __launch_bounds__(V2_LB_T, 1) k2v2_align(const K2Params P) {
           for (int j = 0; j < 8; ++j) { const int k = k0 + j; hb[j] = (k >= lo && k <= hi) ? max(k, 0) - V2_BIAS : V2_NULL; }
 #pragma unroll
           for (int i = 0; i < 4; ++i) ins1[i] = del1[i] = ins2[i] = del2[i] = 0x80008000u;
-        } else {  // boundary chunk: every read is checked against its source wavefront's live range
-          const int16_t* sb = reinterpret_cast<const int16_t*>(stg) + 8 + (lane << 3);
-          int vi1[8], vd1[8], vi2[8], vd2[8];
+        } else {
+          // boundary chunk: elements outside their source wavefront's live range are overwritten with nulls in the staged
+          // copy (lane L owns unit L of every row, lanes 0 / 31 also the unit left / right of the chunk), then the chunk
+          // runs the packed recurrence like an interior one.  A diagonal outside this wavefront's own [lo, hi] has every
+          // source out of range by construction (lo / hi are the union of the shifted source ranges).
+          {
+            unsigned char* sw = const_cast<unsigned char*>(stg);
+            const int c0 = kbase - (gb << 3) + 8;  // staged element position of diagonal k: k + c0 (0 .. 271)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int k = k0 + j;
-            const bool act = k >= lo && k <= hi;
-            const int vmx = (act && in_rng(k, K2_SR_MX)) ? (int)sb[K2_SR_MX * V2_ROWE + j] : V2_NULL;
-            const int i1o = (act && in_rng(k - 1, K2_SR_MO1)) ? (int)sb[K2_SR_MO1 * V2_ROWE + j - 1] : V2_NULL;
-            const int d1o = (act && in_rng(k + 1, K2_SR_MO1)) ? (int)sb[K2_SR_MO1 * V2_ROWE + j + 1] : V2_NULL;
-            const int i1e = (act && in_rng(k - 1, K2_SR_I1E)) ? (int)sb[K2_SR_I1E * V2_ROWE + j - 1] : V2_NULL;
-            const int d1e = (act && in_rng(k + 1, K2_SR_D1E)) ? (int)sb[K2_SR_D1E * V2_ROWE + j + 1] : V2_NULL;
-            const int i2o = (act && in_rng(k - 1, K2_SR_MO2)) ? (int)sb[K2_SR_MO2 * V2_ROWE + j - 1] : V2_NULL;
-            const int d2o = (act && in_rng(k + 1, K2_SR_MO2)) ? (int)sb[K2_SR_MO2 * V2_ROWE + j + 1] : V2_NULL;
-            const int i2e = (act && in_rng(k - 1, K2_SR_I2E)) ? (int)sb[K2_SR_I2E * V2_ROWE + j - 1] : V2_NULL;
-            const int d2e = (act && in_rng(k + 1, K2_SR_D2E)) ? (int)sb[K2_SR_D2E * V2_ROWE + j + 1] : V2_NULL;
-            vi1[j] = min(max(i1o, i1e) + 1, V2_CAP); vd1[j] = max(d1o, d1e);
-            vi2[j] = min(max(i2o, i2e) + 1, V2_CAP); vd2[j] = max(d2o, d2e);
-            hb[j] = max(max(max(vi1[j], vi2[j]), max(vd1[j], vd2[j])), vmx + 1);
-          }
+            for (int r = 0; r < 7; ++r) {
+              const int pa = misc[V2_RLO + r] + c0, pb = pa + misc[V2_RCNT + r] - 1;  // live positions pa .. pb
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            ins1[i] = v2_pack(vi1[2 * i], vi1[2 * i + 1]); del1[i] = v2_pack(vd1[2 * i], vd1[2 * i + 1]);
-            ins2[i] = v2_pack(vi2[2 * i], vi2[2 * i + 1]); del2[i] = v2_pack(vd2[2 * i], vd2[2 * i + 1]);
+              for (int part = 0; part < 2; ++part) {
+                if (part == 1 && !(lane == 0 || lane == 31)) continue;
+                const int p0 = part == 0 ? 8 + (lane << 3) : (lane == 0 ? 0 : 264);
+                if (p0 >= pa && p0 + 7 <= pb) continue;  // fully live
+                uint4* u = reinterpret_cast<uint4*>(sw + r * V2_ROWB + p0 * 2);
+                if (p0 + 7 < pa || p0 > pb) { *u = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u); continue; }
+                uint4 v = *u;
+                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int e = p0 + 2 * i;
+                  const bool okl = e >= pa && e <= pb, okh = e + 1 >= pa && e + 1 <= pb;
+                  w[i] = (okl ? (w[i] & 0xFFFFu) : 0x8000u) | (okh ? (w[i] & 0xFFFF0000u) : 0x80000000u);
+                }
+                *u = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            }
+            __syncwarp();
           }
+          V2Src sv;
+          const unsigned char* sb = stg + 16 + (lane << 4);
+          auto ld4 = [&](int r, uint32_t (&o)[4]) { const uint4 v = *reinterpret_cast<const uint4*>(sb + r * V2_ROWB); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; };
+          auto ldw = [&](int r, int off) -> uint32_t { return *reinterpret_cast<const uint32_t*>(sb + r * V2_ROWB + off); };
+          ld4(K2_SR_MX, sv.mx);
+          ld4(K2_SR_MO1, sv.mo1); sv.mo1L = ldw(K2_SR_MO1, -4); sv.mo1R = ldw(K2_SR_MO1, 16);
+          ld4(K2_SR_I1E, sv.i1e); sv.i1eL = ldw(K2_SR_I1E, -4);
+          ld4(K2_SR_D1E, sv.d1e); sv.d1eR = ldw(K2_SR_D1E, 16);
+          ld4(K2_SR_I2E, sv.i2e); sv.i2eL = ldw(K2_SR_I2E, -4);
+          ld4(K2_SR_D2E, sv.d2e); sv.d2eR = ldw(K2_SR_D2E, 16);
+          ld4(K2_SR_MO2, sv.mo2); sv.mo2L = ldw(K2_SR_MO2, -4); sv.mo2R = ldw(K2_SR_MO2, 16);
+          v2_recur8<true, true>(sv, bw, ins1, del1, ins2, del2);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { hb[2 * i] = v2_lo16(bw[i]); hb[2 * i + 1] = v2_hi16(bw[i]); }
         }
         // the gap rows do not depend on the extension: store them first
         if (gact && s > 0) {
@@ -474,35 +493,40 @@ __global__ void __launch_bounds__(V2_LB_T, 1) k2v2_align(const K2Params P) {
           }
         }
         // ---- bounds, extension along matches, termination test (biased offsets: h = hb + BIAS, v = hb - (k - BIAS)) ----
+        // Straight-line code, no branches (selects only): the eight cells' chains interleave.
         uint32_t xw[8];
+        int okm[8];
         const int kb0 = k0 - V2_BIAS;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int kb = kb0 + j;
-          const bool ok = (unsigned)(hb[j] + V2_BIAS) <= (unsigned)tlen && (unsigned)(hb[j] - kb) <= (unsigned)plen;
-          if (!ok) hb[j] = V2_NULL;
-          xw[j] = window8(wp, ok ? hb[j] - kb : 0) ^ window8(wtb, ok ? hb[j] : -V2_BIAS);
+          const int v = hb[j] - (kb0 + j);
+          const int ok = (int)((unsigned)(hb[j] + V2_BIAS) <= (unsigned)tlen) & (int)((unsigned)v <= (unsigned)plen);
+          okm[j] = ok;
+          hb[j] = ok ? hb[j] : V2_NULL;
+          xw[j] = window8(wp, ok ? v : 0) ^ window8(wtb, ok ? hb[j] : -V2_BIAS);
         }
-        bool more = false;
+        int advmax = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const bool valid = hb[j] >= V2_VMIN;
           const int adv = (int)min(((unsigned)(__ffs((int)xw[j]) - 1)) >> 2, 8u);  // equal bases of the window; 8 when xw == 0
-          if (valid) hb[j] += adv;
-          more = more || (valid && xw[j] == 0u);
+          const int a = okm[j] ? adv : 0;
+          hb[j] += a;
+          advmax = max(advmax, a);
         }
-        if (__any_sync(FULL, more)) {  // rare: a run longer than 8 bases (the true diagonal)
+        if (__any_sync(FULL, advmax == 8)) {  // rare: a run longer than 8 bases (the true diagonal)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const bool go = hb[j] >= V2_VMIN && xw[j] == 0u;
+            const bool go = okm[j] != 0 && xw[j] == 0u;
             const int off = k2_extend_more(wp, wt, plen, tlen, k0 + j, go ? hb[j] + V2_BIAS : 0, go, lane);
             if (go) hb[j] = off - V2_BIAS;
           }
         }
-        bool edge = false;
+        // a cell touches the end of a sequence <=> the largest text / pattern position of the eight does (a null cell has
+        // h = -768 and v = -768 - k <= plen - 760: never at an end)
+        int hmax = hb[0], vmax = hb[0] - kb0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) edge = edge || (hb[j] >= V2_VMIN && (hb[j] + V2_BIAS >= tlen || hb[j] - (kb0 + j) >= plen));
-        if (edge) {  // a cell touches the end of a sequence: full ends-free termination test (rare)
+        for (int j = 1; j < 8; ++j) { hmax = max(hmax, hb[j]); vmax = max(vmax, hb[j] - (kb0 + j)); }
+        if (hmax + V2_BIAS >= tlen || vmax >= plen) {  // full ends-free termination test (rare)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (hb[j] >= V2_VMIN) {

@@ -474,6 +474,17 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       if (a.metric == 1) return wide ? (const void*)k2_align<true, int32_t> : (const void*)k2_align<true, int16_t>;
       return wide ? (const void*)k2_align<false, int32_t> : (const void*)k2_align<false, int16_t>;
     };
+    // K2 v2 launch shapes (sfc_k_align2.cuh): 128 threads for small pairs, else SFC_K2_SHAPE = 384 (default), 512 or 256 (x 2 CTAs / SM)
+    auto v2_kernel = [&](int threads) -> const void* {
+      if (threads == 128) return (const void*)k2v2_align<128, 1>;
+      if (threads == 256) return (const void*)k2v2_align<256, 2>;
+      if (threads == 512) return (const void*)k2v2_align<512, 1>;
+      return (const void*)k2v2_align<384, 1>;
+    };
+    int big_threads = K2_LB_T;
+    if (a.metric == 1 && !getenv("SFC_K2_V1")) {
+      if (const char* e = getenv("SFC_K2_SHAPE")) { const int v = atoi(e); if (v == 256 || v == 384 || v == 512) big_threads = v; }
+    }
     std::vector<Job> jobs;
     // small pairs: one 128-thread CTA each
     if (k2l_begin > k2s_begin) jobs.push_back(Job{std::vector<uint32_t>(c->h_order.begin() + k2s_begin, c->h_order.begin() + k2l_begin), 128, 1});
@@ -503,8 +514,8 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       for (int ci = 3; ci >= 0; --ci) {
         if (tmp[ci].empty()) continue;
         std::stable_sort(tmp[ci].begin(), tmp[ci].end(), [](const std::pair<double, uint32_t>& x, const std::pair<double, uint32_t>& y) { return x.first > y.first; });
-        Job j; j.threads = K2_LB_T; j.C = 1 << ci;
-        if (const char* e = getenv("SFC_K2_THREADS")) j.threads = std::max(64, std::min(K2_LB_T, atoi(e)));  // experiment knob
+        Job j; j.threads = big_threads; j.C = 1 << ci;
+        if (const char* e = getenv("SFC_K2_THREADS")) { if (a.metric != 1 || getenv("SFC_K2_V1")) j.threads = std::max(64, std::min(K2_LB_T, atoi(e))); }  // experiment knob (v1 kernel)
         for (auto& t : tmp[ci]) j.list.push_back(t.second);
         j.max_est = tmp[ci].front().first;  // sorted heaviest first
         jobs.push_back(std::move(j));
@@ -560,9 +571,11 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
           pl->stages = st2;
           pl->smem = fixed_sm2 + st2 * per_stage2;
           pl->max_fixed = v2_fixed;
-          CU(cudaFuncSetAttribute(k2v2_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+          const void* kv2 = v2_kernel(threads);
+          CU(cudaFuncSetAttribute(kv2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+          CU(cudaFuncSetAttribute(kv2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
           int occ = 1;
-          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2v2_align, threads, pl->smem));
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kv2, threads, pl->smem));
           occ = std::max(1, occ);
           size_t slots = (size_t)c->sm_count * occ / C;
           if (C > 1) slots = std::max<size_t>(1, slots * 7 / 8);
@@ -651,7 +664,10 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       if (pl.v2) {
-        CU(cudaLaunchKernelEx(&cfg, k2v2_align, P));
+        if (threads == 128) CU(cudaLaunchKernelEx(&cfg, k2v2_align<128, 1>, P));
+        else if (threads == 256) CU(cudaLaunchKernelEx(&cfg, k2v2_align<256, 2>, P));
+        else if (threads == 512) CU(cudaLaunchKernelEx(&cfg, k2v2_align<512, 1>, P));
+        else CU(cudaLaunchKernelEx(&cfg, k2v2_align<384, 1>, P));
       } else if (a.metric == 1) {
         if (pl.wide) CU(cudaLaunchKernelEx(&cfg, k2_align<true, int32_t>, P)); else CU(cudaLaunchKernelEx(&cfg, k2_align<true, int16_t>, P));
       } else {
@@ -746,12 +762,12 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       for (int cc = 8; cc > 1; cc >>= 1)
         if (retry.size() * (size_t)cc <= (size_t)c->sm_count * 7 / 8) { Cr = cc; break; }
       if (force_c_env > 0) Cr = force_c_env;
-      if ((rc = plan_job(retry, K2_LB_T, Cr, avail, divisor, &pl))) return rc;
+      if ((rc = plan_job(retry, big_threads, Cr, avail, divisor, &pl))) return rc;
       if ((rc = ensure(c, c->d_ws, pl.slab * pl.n_cl))) return rc;
       cur = retry;
       CU(cudaMemcpyAsync((uint32_t*)c->d_order.p + k2s_begin, retry.data(), retry.size() * 4, cudaMemcpyHostToDevice, c->stream));
       CU(cudaMemsetAsync(misc + 8, 0, 4, c->stream));
-      if ((rc = launch_job((const uint32_t*)c->d_order.p + k2s_begin, retry.size(), K2_LB_T, Cr, pl, (unsigned char*)c->d_ws.p, misc + 8, c->stream))) return rc;
+      if ((rc = launch_job((const uint32_t*)c->d_order.p + k2s_begin, retry.size(), big_threads, Cr, pl, (unsigned char*)c->d_ws.p, misc + 8, c->stream))) return rc;
       if (pl.n_cl == 1 && pl.slab >= avail - 4096 && !pool_short) divisor = 1 << 20;  // last resort was tried
     }
   }
