@@ -145,6 +145,11 @@ int sfc_aligner_align(sfc_aligner*, const uint8_t* pattern, size_t len, int mode
                       int32_t* score, int* has_alignment, int64_t* ref_offset,
                       uint32_t* cigar, size_t cigar_cap, size_t* n_cigar);
 
+/* Debug view of the LAST sfc_aligner_align call: gapped pattern, '|' under matches, gapped text (wfa2_utils.rs:253-273:
+ * PairwiseAligner::matching / print_pairwise_alignment), in the order the sequences were aligned (both reversed).
+ * *len = characters per line; SFC_ERR_CAPACITY (with *len set) when cap is too small. */
+int sfc_aligner_matching(sfc_aligner*, char* pattern_line, char* mid_line, char* text_line, size_t cap, size_t* len);
+
 /* ---- multi-GPU sharding helpers (host only; no collective: batches are independent) ----
  * The unit of sharding is the SV group / breakpoint cluster, the reference's own rayon task granularity
  * (src/joint_call/joint_call_all_samples.rs:127-142, src/refine_sv/mod.rs:861-887). */

@@ -60,6 +60,8 @@ extern "C" {
     pub fn sfc_aligner_align(a: *mut SfcAligner, pattern: *const u8, len: usize, mode: i32,
                              text_clip_frac: f64, pattern_clip_frac: f64, score: *mut i32, has_alignment: *mut i32,
                              ref_offset: *mut i64, cigar: *mut u32, cigar_cap: usize, n_cigar: *mut usize) -> i32;
+    pub fn sfc_aligner_matching(a: *mut SfcAligner, pattern_line: *mut c_char, mid_line: *mut c_char, text_line: *mut c_char,
+                                cap: usize, len: *mut usize) -> i32;
     pub fn sfc_estimate_pair_work(pen: *const SfcPenalties, pairs: *const SfcPair, n: usize, work: *mut u64) -> i32;
     pub fn sfc_shard_plan(group_work: *const u64, n_groups: usize, n_shards: i32, shard_of_group: *mut u32) -> i32;
     pub fn sfc_bio_align_batch(ctx: *mut SfcCtx, scoring: *const SfcBioScoring, arena: *const u8, arena_len: usize,

@@ -46,7 +46,7 @@ EXPORTS = [
     "sfc_align_batch", "sfc_batch_upload", "sfc_batch_run", "sfc_batch_download", "sfc_batch_get_stats",
     "sfc_expand_ops", "sfc_translate_cigar", "sfc_translate_rle",
     "sfc_aligner_new_consensus", "sfc_aligner_new_large_indel", "sfc_aligner_free", "sfc_aligner_set_text",
-    "sfc_aligner_align", "sfc_measure_int_peak", "sfc_estimate_pair_work", "sfc_shard_plan", "sfc_multi_create", "sfc_multi_destroy",
+    "sfc_aligner_align", "sfc_aligner_matching", "sfc_measure_int_peak", "sfc_estimate_pair_work", "sfc_shard_plan", "sfc_multi_create", "sfc_multi_destroy",
     "sfc_multi_device_count", "sfc_multi_last_error", "sfc_multi_align_batch", "sfc_multi_last_kernel_ms",
     "sfc_bio_align_batch", "sfc_bio_score_batch",
 ]
@@ -99,6 +99,7 @@ def lib():
     L.sfc_aligner_set_text.argtypes = [vp, u8p, C.c_size_t]
     L.sfc_aligner_align.argtypes = [vp, u8p, C.c_size_t, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int), i64p, u32p, C.c_size_t, szp]
+    L.sfc_aligner_matching.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, szp]
     L.sfc_measure_int_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.sfc_estimate_pair_work.argtypes = [C.POINTER(Penalties), vp, C.c_size_t, vp]
     L.sfc_shard_plan.argtypes = [vp, C.c_size_t, C.c_int, vp]

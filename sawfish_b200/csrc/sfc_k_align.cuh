@@ -67,6 +67,10 @@ struct K2Params {
   int stages;   // cp.async stages per warp for the interior chunks (0 = load straight from global; int32 rings only)
   int max_score;
   unsigned long long* prof;  // optional phase timers (clock64 of thread 0): [0] cell loop [1] barriers+trim [2] backtrace [3] setup
+  // K2 v2 (sfc_k_align2.cuh): the wavefront history of every resident pair lives in pages of one shared pool
+  unsigned char* pages;  // n_pages pages of (1 << page_shift) bytes
+  int page_shift, n_pages;
+  int* pgstack;         // [0] lock, [1] free pages, [2 ..] their ids
 };
 
 struct K2Range {

@@ -8,8 +8,9 @@
 //     bases fits (the pattern may be longer); longer texts go to the int32 kernel.  Eight diagonals per thread, two per
 //     register: the recurrence runs on packed s16x2 DPX instructions (VIMNMX / VIMNMX3 / VIADDMNMX .S16x2, 7 per cell
 //     instead of 27), only the match extension is scalar;
-//   * every wavefront of every component is KEPT (append-only rows in the CTA's slab of device memory: 10 B per cell —
-//     what WFA2's MemoryHigh does, laid out for 180 GB of HBM) instead of ring rows + one choice byte per cell.  Nothing
+//   * every wavefront of every component is KEPT (append-only rows, 10 B per cell — what WFA2's MemoryHigh does, laid
+//     out for 180 GB of HBM: one pool of 8 MB pages shared by every resident pair, a pair takes pages as its history
+//     grows and returns them when it is done) instead of ring rows + one choice byte per cell.  Nothing
 //     is recorded at compute time: the backtrace re-derives each decision on its path from the stored source values
 //     with the compute-time formula (same inputs, same tie-break order X > D2 > D1 > I2 > I1, extend >= open), a warp
 //     at a time (nine candidates of an M step in parallel, 32 speculative steps of a gap run per round trip);
@@ -35,7 +36,9 @@ enum { V2_S = 4, V2_STATUS, V2_LO, V2_HI, V2_HAS2, V2_G1A, V2_G1B, V2_G2A, V2_G2
        V2_Q = 20 /* 7 source + 5 output rows: virtual origin in 16-byte units */, V2_RLO = 32 /* 7 */, V2_RCNT = 39 /* 7 */,
        V2_SG0 = 46 /* 7: first stored unit of each source row */, V2_SNG = 53 /* 7: stored units */, V2_OSLOT = 60 /* 5 */,
        V2_CLO = 65 /* 5 */, V2_CHI = 70 /* 5 */, V2_D64 = 76 /* two u64: units used, cells */, V2_TAB = 80 /* [32][5] */,
-       V2_WIDE = 240 /* 10 */, V2_CAND = 250 /* 10 */ };
+       V2_WIDE = 240 /* 10 */, V2_CAND = 250 /* 10 */, V2_PGSEQ = 260 /* 4: ring of this pair's page ids (rank 0's copy is read) */,
+       V2_PGI = 264 /* index of the current page in that sequence */, V2_PGN = 265 /* pages acquired (rank 0) */, V2_NEED = 266 /* 64-byte units of this score's rows */,
+       V2_NUP = 267 /* 64-byte units per row (padded) */ };
 
 // ---- packed s16x2 helpers: DPX on the device, plain C++ on the host (tests/cpp/test_v2_recur.cu) ----
 #if defined(__CUDA_ARCH__)
@@ -117,10 +120,35 @@ __device__ __forceinline__ uint32_t v2_renull(uint32_t w) {
   const int l = v2_lo16(w), h = v2_hi16(w);
   return v2_pack(l < V2_VMIN ? V2_NULL : l, h < V2_VMIN ? V2_NULL : h);
 }
+#define V2_ROW(R, q, g) ((R) + (((long long)(q) << 2) + (long long)(g)))
 __device__ __forceinline__ void v2_cp16(unsigned dst_smem, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(gsrc) : "memory");
 }
 
+// ---- page pool (one thread at a time behind a spin lock; a pair takes a page every few dozen scores) ----
+__device__ __forceinline__ void v2_pool_lock(int* st) { while (atomicCAS(st, 0, 1) != 0) __nanosleep(64); __threadfence(); }
+__device__ __forceinline__ void v2_pool_unlock(int* st) { __threadfence(); atomicExch(st, 0); }
+__device__ __forceinline__ int v2_page_acquire(int* st) {  // -1: the pool is empty (the pair fails with SFC_STATUS_OOM and is re-run later)
+  v2_pool_lock(st);
+  volatile int* v = st;
+  const int n = v[1];
+  int id = -1;
+  if (n > 0) { id = v[1 + n]; v[1] = n - 1; }
+  v2_pool_unlock(st);
+  return id;
+}
+__device__ __forceinline__ void v2_pages_release(int* st, const int* list, int cnt) {
+  if (cnt <= 0) return;
+  v2_pool_lock(st);
+  volatile int* v = st;
+  int n = v[1];
+  for (int i = 0; i < cnt; ++i) { const int id = list[i]; if (id >= 0) { v[2 + n] = id; ++n; } }
+  v[1] = n;
+  v2_pool_unlock(st);
+}
+
+// Row addressing: a row's origin q is in 64-byte units from the pool base (32 bit: 128 GB), a diagonal group g in 16-byte
+// units from the origin: address = pool + q * 64 + g * 16.
 // Interior chunk: lane L copies unit gb+L of every needed row; lanes 0 / 31 also the unit left / right of the chunk for
 // the rows read at k-1 / k+1.  One asm block per group of copies so that every source address has its own register
 // pair (see k2_stage_issue).
@@ -136,8 +164,8 @@ __device__ __forceinline__ void v2_stage_fast(unsigned char* stg, const int4* __
       " @p2 cp.async.cg.shared.global [%0+2176], [%5], 16;\n"
       " @p2 cp.async.cg.shared.global [%0+2720], [%6], 16;\n"
       " @pm cp.async.cg.shared.global [%0+3264], [%7], 16;\n}"
-      ::"r"(d), "l"(R + (q[K2_SR_MX] + g)), "l"(R + (q[K2_SR_MO1] + g)), "l"(R + (q[K2_SR_I1E] + g)), "l"(R + (q[K2_SR_D1E] + g)),
-        "l"(R + (q[K2_SR_I2E] + g)), "l"(R + (q[K2_SR_D2E] + g)), "l"(R + (q[K2_SR_MO2] + g)), "r"((int)has2), "r"((int)(has2 && mo2))
+      ::"r"(d), "l"(V2_ROW(R, q[K2_SR_MX], g)), "l"(V2_ROW(R, q[K2_SR_MO1], g)), "l"(V2_ROW(R, q[K2_SR_I1E], g)), "l"(V2_ROW(R, q[K2_SR_D1E], g)),
+        "l"(V2_ROW(R, q[K2_SR_I2E], g)), "l"(V2_ROW(R, q[K2_SR_D2E], g)), "l"(V2_ROW(R, q[K2_SR_MO2], g)), "r"((int)has2), "r"((int)(has2 && mo2))
       : "memory");
   if (lane == 0 || lane == 31) {
     const bool left = lane == 0;
@@ -151,8 +179,8 @@ __device__ __forceinline__ void v2_stage_fast(unsigned char* stg, const int4* __
         " cp.async.cg.shared.global [%2], [%3], 16;\n"
         " @p2 cp.async.cg.shared.global [%4], [%5], 16;\n"
         " @pm cp.async.cg.shared.global [%6], [%7], 16;\n}"
-        ::"r"(dx + K2_SR_MO1 * V2_ROWB), "l"(R + (q[K2_SR_MO1] + g + xo)), "r"(dx + r1 * V2_ROWB), "l"(R + (q1 + g + xo)),
-          "r"(dx + r2 * V2_ROWB), "l"(R + (q2 + g + xo)), "r"(dx + K2_SR_MO2 * V2_ROWB), "l"(R + (q[K2_SR_MO2] + g + xo)),
+        ::"r"(dx + K2_SR_MO1 * V2_ROWB), "l"(V2_ROW(R, q[K2_SR_MO1], g + xo)), "r"(dx + r1 * V2_ROWB), "l"(V2_ROW(R, q1, g + xo)),
+          "r"(dx + r2 * V2_ROWB), "l"(V2_ROW(R, q2, g + xo)), "r"(dx + K2_SR_MO2 * V2_ROWB), "l"(V2_ROW(R, q[K2_SR_MO2], g + xo)),
           "r"((int)has2), "r"((int)(has2 && mo2))
         : "memory");
   }
@@ -167,10 +195,10 @@ __device__ __forceinline__ void v2_stage_guarded(unsigned char* stg, const int4*
 #pragma unroll
   for (int r = 0; r < 7; ++r) {
     const int g0 = misc[V2_SG0 + r], ng = misc[V2_SNG + r];
-    if ((unsigned)(g - g0) < (unsigned)ng) v2_cp16(d + r * V2_ROWB, R + (q[r] + g));
+    if ((unsigned)(g - g0) < (unsigned)ng) v2_cp16(d + r * V2_ROWB, V2_ROW(R, q[r], g));
     if (r != K2_SR_MX) {
-      if (lane == 0 && (unsigned)(g - 1 - g0) < (unsigned)ng) v2_cp16(d - 16u + r * V2_ROWB, R + (q[r] + g - 1));
-      if (lane == 31 && (unsigned)(g + 1 - g0) < (unsigned)ng) v2_cp16(d + 16u + r * V2_ROWB, R + (q[r] + g + 1));
+      if (lane == 0 && (unsigned)(g - 1 - g0) < (unsigned)ng) v2_cp16(d - 16u + r * V2_ROWB, V2_ROW(R, q[r], g - 1));
+      if (lane == 31 && (unsigned)(g + 1 - g0) < (unsigned)ng) v2_cp16(d + 16u + r * V2_ROWB, V2_ROW(R, q[r], g + 1));
     }
   }
 }
@@ -197,10 +225,21 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
   long long t_cells = 0, t_sync = 0, t_bt = 0, t_setup = 0, t_trim = 0, t_plan = 0, t_mark = clock64();
 #define V2_TICK(acc) do { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; } while (0)
 
+  if (tid == 0) misc[V2_PGN] = 0;
   for (;;) {
     csync();
     V2_TICK(t_bt);
-    if (crank == 0 && tid == 0) { misc[0] = (int)atomicAdd(P.counter, 1u); misc[1] = misc[2] = INT_MAX; }
+    if (crank == 0 && tid == 0) {
+      int* pglist = reinterpret_cast<int*>(slab);
+      v2_pages_release(P.pgstack, pglist, misc[V2_PGN]);  // the previous pair's history
+      misc[V2_PGN] = 0;
+      misc[0] = (int)atomicAdd(P.counter, 1u); misc[1] = misc[2] = INT_MAX;
+      if ((uint32_t)misc[0] < P.n) {  // the first two pages of the next pair (the second one is the reserve, see plan)
+        const int p0 = v2_page_acquire(P.pgstack), p1 = v2_page_acquire(P.pgstack);
+        pglist[0] = p0; pglist[1] = p1; misc[V2_PGN] = 2;
+        misc[V2_PGSEQ] = p0; misc[V2_PGSEQ + 1] = p1; misc[V2_PGSEQ + 2] = misc[V2_PGSEQ + 3] = -1;
+      }
+    }
     csync();
     const uint32_t wi = (uint32_t)misc0[0];
     if (wi >= P.n) { csync(); break; }
@@ -218,20 +257,22 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
     const size_t hist_bytes = (((size_t)S_cap + 1) * V2_HIST * 4 + 15) & ~(size_t)15;
     const size_t E_cap = (size_t)plen + tlen + 8;
     const size_t tmp_bytes = (E_cap * 4 + 15) & ~(size_t)15;
-    const size_t fixed = hist_bytes + 2 * tmp_bytes;
+    const size_t pgl_bytes = ((size_t)P.n_pages * 4 + 15) & ~(size_t)15;  // this slot's list of pages taken (for the release)
+    const size_t fixed = pgl_bytes + hist_bytes + 2 * tmp_bytes;
     int res_status = 0, res_score = 0;
     if (nwp + nwt > P.win_cap || tlen > V2_MAX_TLEN) res_status = -5;
-    else if (fixed + 4096 > P.slab_bytes) res_status = -6;
+    else if (fixed > P.slab_bytes) res_status = -6;
     if (res_status != 0) {
       if (crank == 0 && tid == 0) { P.scores[pi] = 0; P.status[pi] = res_status; P.out_len[pi] = 0; P.out_off[pi] = 0; }
       continue;
     }
-    int* hist = reinterpret_cast<int*>(slab);  // [S_cap+1][16]: exists, M-row origin, units per row, first unit, lo/hi x 5
-    uint32_t* tmp_b = reinterpret_cast<uint32_t*>(slab + hist_bytes);
+    int* pglist = reinterpret_cast<int*>(slab);
+    int* hist = reinterpret_cast<int*>(slab + pgl_bytes);  // [S_cap+1][16]: exists, M-row origin, 64-byte units per row, first unit, lo/hi x 5
+    uint32_t* tmp_b = reinterpret_cast<uint32_t*>(slab + pgl_bytes + hist_bytes);
     uint32_t* tmp_f = tmp_b + (tmp_bytes >> 2);
-    int16_t* rows16 = reinterpret_cast<int16_t*>(slab + fixed);
-    const int4* rowsU = reinterpret_cast<const int4*>(slab + fixed);
-    const unsigned long long cap_u = (P.slab_bytes - fixed) >> 4;  // 16-byte units available for rows
+    int16_t* rows16 = reinterpret_cast<int16_t*>(P.pages);
+    const int4* rowsU = reinterpret_cast<const int4*>(P.pages);
+    const int pu64 = 1 << (P.page_shift - 6);  // 64-byte units per page
     {
       const uint32_t* gp = P.nib + pr.p_woff;
       const uint32_t* gt = P.nib + pr.t_woff;
@@ -243,7 +284,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
     const int sbM = 0, sbI1 = P.nM, sbD1 = P.nM + P.nG1, sbI2 = P.nM + 2 * P.nG1, sbD2 = P.nM + 2 * P.nG1 + P.nG2;
     unsigned long long* D64 = reinterpret_cast<unsigned long long*>(misc + V2_D64);  // [0] row units used, [1] cells
     // element of row-origin q (16-byte units) at diagonal k
-    auto rd = [&](int q, int k) -> int { return (int)__ldcg(rows16 + (long long)q * 8 + (k + kbase)); };
+    auto rd = [&](int q, int k) -> int { return (int)__ldcg(rows16 + (long long)q * 32 + (k + kbase)); };
     auto in_mat = [&](int vb, int k) -> bool { return k2_in_matrix(vb + V2_BIAS, k, plen, tlen); };
 
     // ---- per-score plan (warp 0, lane r = row r: 0..6 sources MX, MO1, I1E, D1E, I2E, D2E, MO2; 7..11 outputs) ----
@@ -254,7 +295,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
       const int dl = (int)(signed char)(dpk & 0xFF), dh = (int)(signed char)((dpk >> 8) & 0xFF);
       const int il = (int)(signed char)((dpk >> 16) & 0xFF), ih = (int)(signed char)((dpk >> 24) & 0xFF);
       const bool is_src = lane < 7, is_out = lane >= 7 && lane < 12;
-      const unsigned long long used = D64[0];
+      int used = (int)D64[0], pgi = misc[V2_PGI];  // 64-byte units taken in the current page, its index in the pair's page sequence
       for (int sN = s_from;; ++sN) {
         if (sN > S_cap) { if (lane == 0) misc[V2_STATUS] = -7; break; }
         const int sc = sN - back;
@@ -283,8 +324,19 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
         if ((anym & set1) != set1 || sN == 0) { ilo = 1; ihi = 0; }
         if (!has2 || (anym & set2) != set2 || sN == 0) { ilo_b = 1; ihi_b = 0; }
         const int flo = max(ilo, lo), fhi = min(ihi, hi), flo_b = max(ilo_b, lo), fhi_b = min(ihi_b, hi);
-        const int g_lo = (lo + kbase) >> 3, g_hi = (hi + kbase) >> 3, nu = g_hi - g_lo + 1;
-        if (used + 5ull * (unsigned long long)nu > cap_u) { if (lane == 0) misc[V2_STATUS] = -6; break; }
+        // rows start on 64-byte boundaries: first unit a multiple of 4, row pitch a multiple of 4 units
+        const int g_lo = ((lo + kbase) >> 3) & ~3, g_hi = (hi + kbase) >> 3, nu = g_hi - g_lo + 1, nup = (nu + 3) >> 2;
+        const int need = 5 * nup;
+        const bool sw = used + need > pu64;  // the rows of a score never straddle pages: move to the reserve page
+        if (sw) { ++pgi; used = 0; }
+        const int page = misc0[V2_PGSEQ + (pgi & 3)];  // published by rank 0 at least one cluster barrier ago
+        if (need > pu64 || page < 0) { if (lane == 0) misc[V2_STATUS] = -6; break; }
+        if (sw && lane == 0 && crank == 0) {  // take the next reserve page now: it is first needed at a later score
+          const int np = v2_page_acquire(P.pgstack);
+          if (np >= 0 && misc[V2_PGN] < P.n_pages) { pglist[misc[V2_PGN]] = np; misc[V2_PGN] += 1; }
+          misc[V2_PGSEQ + ((pgi + 1) & 3)] = np;
+        }
+        const int base64 = page * pu64 + used;
         const int m2lo = __shfl_sync(FULL, rlo, K2_SR_MO2), m2hi = __shfl_sync(FULL, rhi, K2_SR_MO2);
         if (lane < 7) {
           misc[V2_Q + lane] = rq; misc[V2_RLO + lane] = rlo; misc[V2_RCNT + lane] = max(rhi - rlo + 1, 0);
@@ -292,7 +344,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
         }
         if (is_out) {
           const int c = lane - 7;
-          const int qo = (int)(used + (unsigned long long)c * (unsigned long long)nu) - g_lo;
+          const int qo = base64 + c * nup - (g_lo >> 2);
           misc[V2_Q + lane] = qo; misc[V2_OSLOT + c] = slot;
           meta[5 * slot + 2] = qo; meta[5 * slot + 3] = g_lo; meta[5 * slot + 4] = nu;  // lo / hi follow at trim time
         }
@@ -308,6 +360,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
         }
         if (lane == 0) {
           misc[V2_S] = sN; misc[V2_LO] = lo; misc[V2_HI] = hi; misc[V2_HAS2] = has2; misc[V2_G0] = g_lo; misc[V2_NU] = nu;
+          misc[V2_NEED] = need; misc[V2_NUP] = nup; misc[V2_PGI] = pgi; D64[0] = (unsigned long long)used;
           misc[V2_RENORM] = (sN & 255) == 0;
           // chunk kinds as ranges of the chunk's first unit gb (chunk diagonals 8*gb - kbase .. + 255)
           const bool e1 = flo + 255 > fhi, e2 = flo_b + 255 > fhi_b;
@@ -323,7 +376,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
       __syncwarp();
     };
     if (warp == 0) {
-      if (lane == 0) { misc[V2_STATUS] = 0; D64[0] = 0; D64[1] = 0; misc[V2_ANYW] = 0; }
+      if (lane == 0) { misc[V2_STATUS] = 0; D64[0] = 0; D64[1] = 0; misc[V2_ANYW] = 0; misc[V2_PGI] = 0; }
       if (lane < 10) { misc[V2_WIDE + lane] = 0; misc[V2_CAND + lane] = (lane & 1) ? INT_MIN : INT_MAX; }
       {
         int comp = K2_C_M, back = 0, dl = 0, dh = 0, il = 0, ih = 0;
@@ -370,7 +423,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
 #pragma unroll
       for (int r = 0; r < 7; ++r) qs[r] = misc[V2_Q + r];
       const int qM = misc[V2_Q + 7], qI1 = misc[V2_Q + 8], qD1 = misc[V2_Q + 9], qI2 = misc[V2_Q + 10], qD2 = misc[V2_Q + 11];
-      int4* outU = reinterpret_cast<int4*>(slab + fixed);
+      int4* outU = reinterpret_cast<int4*>(P.pages);
+      const int nup = misc[V2_NUP];
       int term_k = INT_MAX;
 
       auto kind_of = [&](int gb) -> int {
@@ -485,11 +539,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) { ins1[i] = v2_renull(ins1[i]); ins2[i] = v2_renull(ins2[i]); }
           }
-          outU[qI1 + g] = make_int4((int)ins1[0], (int)ins1[1], (int)ins1[2], (int)ins1[3]);
-          outU[qD1 + g] = make_int4((int)del1[0], (int)del1[1], (int)del1[2], (int)del1[3]);
+          *V2_ROW(outU, qI1, g) = make_int4((int)ins1[0], (int)ins1[1], (int)ins1[2], (int)ins1[3]);
+          *V2_ROW(outU, qD1, g) = make_int4((int)del1[0], (int)del1[1], (int)del1[2], (int)del1[3]);
           if (has2) {
-            outU[qI2 + g] = make_int4((int)ins2[0], (int)ins2[1], (int)ins2[2], (int)ins2[3]);
-            outU[qD2 + g] = make_int4((int)del2[0], (int)del2[1], (int)del2[2], (int)del2[3]);
+            *V2_ROW(outU, qI2, g) = make_int4((int)ins2[0], (int)ins2[1], (int)ins2[2], (int)ins2[3]);
+            *V2_ROW(outU, qD2, g) = make_int4((int)del2[0], (int)del2[1], (int)del2[2], (int)del2[3]);
           }
         }
         // ---- bounds, extension along matches, termination test (biased offsets: h = hb + BIAS, v = hb - (k - BIAS)) ----
@@ -535,7 +589,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
             }
           }
         }
-        if (gact) outU[qM + g] = make_int4((int)v2_pack(hb[0], hb[1]), (int)v2_pack(hb[2], hb[3]), (int)v2_pack(hb[4], hb[5]), (int)v2_pack(hb[6], hb[7]));
+        if (gact) *V2_ROW(outU, qM, g) = make_int4((int)v2_pack(hb[0], hb[1]), (int)v2_pack(hb[2], hb[3]), (int)v2_pack(hb[4], hb[5]), (int)v2_pack(hb[6], hb[7]));
       }
       k2_cp_wait<0>();
       V2_TICK(t_cells);
@@ -549,7 +603,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
         end_k = tk; done = true;
         if (crank == 0 && tid == 0) {
           int* h = hist + (size_t)s * V2_HIST;
-          h[0] = 1; h[1] = qM; h[2] = nu; h[3] = g_lo;  // the final wavefront is only read at (s, end_k) itself
+          h[0] = 1; h[1] = qM; h[2] = nup; h[3] = g_lo;  // the final wavefront is only read at (s, end_k) itself
           D64[1] += (unsigned long long)(hi - lo + 1);
         }
         break;
@@ -656,14 +710,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
           int v = 0;
           if (lane == 0) v = 1;
           else if (lane == 1) v = qM;
-          else if (lane == 2) v = nu;
+          else if (lane == 2) v = nup;
           else if (lane == 3) v = g_lo;
           else if (lane < 14) v = meta[5 * misc[V2_OSLOT + ((lane - 4) >> 1)] + ((lane - 4) & 1)];
           hist[(size_t)s * V2_HIST + lane] = v;
         }
         if (lane == 0) {
           D64[1] += (unsigned long long)(hi - lo + 1);
-          D64[0] += 5ull * (unsigned long long)nu;
+          D64[0] += (unsigned long long)misc[V2_NEED];
         }
         __syncwarp();
         V2_TICK(t_trim);

@@ -53,6 +53,8 @@ struct sfc_ctx {
   size_t ws_limit = 0;
   // device buffers
   DevBuf d_arena, d_nib, d_seqs, d_seqwoff, d_pairs, d_order, d_scores, d_status, d_misc, d_pool, d_outoff, d_outlen, d_ws;
+  DevBuf d_pages, d_pgstack;  // K2 v2: the page pool of the wavefront history and its free stack
+  std::vector<int> h_pgstack;
   DevBuf d_b_arena, d_b_pairs, d_b_out, d_b_pool;  // K4 (bio aligner) staging; the slabs reuse d_ws
   // batch state
   size_t n_pairs = 0;
@@ -74,6 +76,9 @@ struct sfc_aligner {
   sfc_ctx* ctx;
   sfc_penalties pen;
   std::vector<uint8_t> text;
+  // the last alignment, for the debug view (sfc_aligner_matching): run-length ops + the pattern they refer to
+  std::vector<uint32_t> last_ops;
+  std::vector<uint8_t> last_pattern;
 };
 
 namespace {
@@ -246,7 +251,7 @@ extern "C" void sfc_destroy(sfc_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->d_arena, &c->d_nib, &c->d_seqs, &c->d_seqwoff, &c->d_pairs, &c->d_order, &c->d_scores, &c->d_status,
-                    &c->d_misc, &c->d_pool, &c->d_outoff, &c->d_outlen, &c->d_ws, &c->d_b_arena, &c->d_b_pairs, &c->d_b_out,
+                    &c->d_misc, &c->d_pool, &c->d_outoff, &c->d_outlen, &c->d_ws, &c->d_pages, &c->d_pgstack, &c->d_b_arena, &c->d_b_pairs, &c->d_b_out,
                     &c->d_b_pool})
     release(*b);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -460,7 +465,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
   if (k2s_begin < n) {
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    size_t avail = (size_t)((double)(free_b + c->d_ws.cap + c->d_pool.cap) * 0.85);
+    size_t avail = (size_t)((double)(free_b + c->d_ws.cap + c->d_pool.cap + c->d_pages.cap) * 0.85);
     if (c->ws_limit && avail > c->ws_limit) avail = c->ws_limit;
     size_t pool_cap = want_cigar ? std::max<size_t>((n - k2s_begin) * 64, (size_t)1 << 20) : 16;
     if ((rc = ensure(c, c->d_pool, pool_cap * 4))) return rc;
@@ -474,16 +479,26 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       if (a.metric == 1) return wide ? (const void*)k2_align<true, int32_t> : (const void*)k2_align<true, int16_t>;
       return wide ? (const void*)k2_align<false, int32_t> : (const void*)k2_align<false, int16_t>;
     };
-    // K2 v2 launch shapes (sfc_k_align2.cuh): 128 threads for small pairs, else SFC_K2_SHAPE = 384 (default), 512 or 256 (x 2 CTAs / SM)
-    auto v2_kernel = [&](int threads) -> const void* {
+    // K2 v2 launch shapes (sfc_k_align2.cuh): 128 threads for small pairs; for the rest SFC_K2_SHAPE = "threads[,CTAs per SM]"
+    // picks one of the compiled (threads, CTAs / SM) variants (default 384 x 1)
+    auto v2_kernel = [&](int threads, int minb) -> const void* {
       if (threads == 128) return (const void*)k2v2_align<128, 1>;
       if (threads == 256) return (const void*)k2v2_align<256, 2>;
+      if (threads == 320) return (const void*)k2v2_align<320, 2>;
       if (threads == 512) return (const void*)k2v2_align<512, 1>;
+      if (threads == 384 && minb >= 2) return (const void*)k2v2_align<384, 2>;
       return (const void*)k2v2_align<384, 1>;
     };
-    int big_threads = K2_LB_T;
+    int big_threads = K2_LB_T, big_minb = 1;
     if (a.metric == 1 && !getenv("SFC_K2_V1")) {
-      if (const char* e = getenv("SFC_K2_SHAPE")) { const int v = atoi(e); if (v == 256 || v == 384 || v == 512) big_threads = v; }
+      if (const char* e = getenv("SFC_K2_SHAPE")) {
+        int t = 0, b = 0;
+        const int got = sscanf(e, "%d,%d", &t, &b);
+        if (got >= 1 && (t == 256 || t == 320 || t == 384 || t == 512)) {
+          big_threads = t;
+          big_minb = (t == 256 || t == 320) ? 2 : (t == 384 && got >= 2 && b >= 2) ? 2 : 1;
+        }
+      }
     }
     std::vector<Job> jobs;
     // small pairs: one 128-thread CTA each
@@ -501,7 +516,14 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       }
       int force_c = 0;
       if (const char* e = getenv("SFC_K2_CLUSTER")) force_c = atoi(e);
-      const double share = std::max(total / (double)c->sm_count, 2e6);
+      double share = std::max(total / (double)c->sm_count, 2e6);
+      if (a.metric == 1 && !getenv("SFC_K2_V1")) {
+        // K2 v2 keeps 10 B of wavefront history per cell (budgeted at 1.5 x the estimate): a pair whose history does not
+        // fit one resident CTA's share of device memory is spread over a cluster, whose slab is that many shares
+        const int occ_guess = big_minb;
+        const double mem_share = (double)avail * 0.80 / ((double)c->sm_count * occ_guess) / 15.0;
+        share = std::min(share, std::max(mem_share, 2e6));
+      }
       std::vector<uint32_t> byc[4];
       std::vector<std::pair<double, uint32_t>> tmp[4];
       for (size_t q = 0; q < nl; ++q) {
@@ -523,7 +545,10 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     }
 
     // size one job's launch: returns grid (in clusters), slab bytes, shared bytes, win_cap
-    struct Plan { size_t n_cl, slab, smem, max_fixed; int win_cap, stages; bool wide; bool v2; };
+    struct Plan { size_t n_cl, slab, smem, max_fixed, rows_want; int win_cap, stages; bool wide; bool v2; };
+    constexpr int kPageShift = 23;          // 8 MB pages
+    constexpr size_t kMaxPages = 15360;     // 120 GB: row origins are 32-bit counts of 64-byte units
+    size_t v2_pages = 0;                    // pages of the pool of this run (0: no v2 job)
     // max_est: estimated wavefront cells of the heaviest pair of the list (0 = unknown).  One choice byte is kept per cell,
     // so the slab's choice-byte budget follows it: a pair that runs out is re-run from scratch in an escalation pass, at
     // the tail of the batch, which costs far more than the memory does (180 GB of HBM).
@@ -563,7 +588,10 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
         const size_t per_stage2 = (size_t)(threads / 32) * 7 * V2_ROWB;
         int st2 = 2;
         if (const char* e = getenv("SFC_K2_STAGES")) st2 = std::max(1, std::min(3, atoi(e)));
-        while (st2 > 1 && fixed_sm2 + st2 * per_stage2 > c->smem_optin) --st2;
+        // shared memory per CTA such that the variant's CTAs per SM all fit (228 KB per SM, 1 KB reserved per CTA)
+        const int minb = threads == 128 ? 1 : big_minb;
+        const size_t sm_cap = std::min<size_t>(c->smem_optin, ((size_t)228 * 1024) / (size_t)minb - 1024);
+        while (st2 > 1 && fixed_sm2 + st2 * per_stage2 > sm_cap) --st2;
         if (fits && fixed_sm2 + st2 * per_stage2 <= c->smem_optin) {
           pl->v2 = true;
           pl->wide = false;
@@ -571,7 +599,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
           pl->stages = st2;
           pl->smem = fixed_sm2 + st2 * per_stage2;
           pl->max_fixed = v2_fixed;
-          const void* kv2 = v2_kernel(threads);
+          const void* kv2 = v2_kernel(threads, minb);
           CU(cudaFuncSetAttribute(kv2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
           CU(cudaFuncSetAttribute(kv2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
           int occ = 1;
@@ -580,18 +608,16 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
           size_t slots = (size_t)c->sm_count * occ / C;
           if (C > 1) slots = std::max<size_t>(1, slots * 7 / 8);
           const size_t n_cl = std::max<size_t>(1, std::min<size_t>(list.size(), slots) / divisor);
-          // rows: 10 B per wavefront cell.  The budget follows the work estimate of the heaviest pair (1.5 x); when the
-          // job's share of device memory cannot hold that for every resident pair the slabs shrink (never the number of
-          // resident pairs) and a pair that runs out is re-run in an escalation pass with a larger share.
-          size_t rows_want = std::max<size_t>((size_t)2048 * max_W * 10 * divisor, (size_t)16 << 20);
+          // rows: 10 B per wavefront cell, in pages of the shared pool (sized below from every job's wish: 1.5 x the work
+          // estimate of its heaviest pair for every resident pair); the slab only holds the per-slot tables
+          size_t rows_want = std::max<size_t>((size_t)2048 * max_W * 10, (size_t)16 << 20);
           if (max_est > 0) rows_want = std::max<size_t>(rows_want, (size_t)(15.0 * max_est) + ((size_t)4 << 20));
-          rows_want = std::min<size_t>(rows_want, (size_t)64 << 30);
-          size_t slab = v2_fixed + rows_want;
+          pl->rows_want = rows_want;
+          size_t slab = (v2_fixed + kMaxPages * 4 + 64 + 255) & ~(size_t)255;
           size_t ncl = n_cl;
-          if (slab * ncl > budget) slab = budget / ncl;
-          while (ncl > 1 && slab < v2_fixed + ((size_t)8 << 20)) { ncl = (ncl + 1) / 2; slab = std::min(v2_fixed + rows_want, budget / ncl); }
-          if (slab < v2_fixed + 4096) return fail(c, SFC_ERR_OOM, "device workspace too small: need %zu B for one pair", v2_fixed);
-          pl->slab = slab & ~(size_t)255;
+          while (ncl > 1 && slab * ncl > budget) ncl = (ncl + 1) / 2;
+          if (slab * ncl > budget) return fail(c, SFC_ERR_OOM, "device workspace too small: need %zu B for one pair", slab);
+          pl->slab = slab;
           pl->n_cl = ncl;
           return 0;
         }
@@ -653,6 +679,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       P.stages = pl.stages;
       P.max_score = INT_MAX / 4;
       P.prof = getenv("SFC_K2_PROF") ? (unsigned long long*)(misc + 40) : nullptr;
+      P.pages = (unsigned char*)c->d_pages.p; P.page_shift = kPageShift; P.n_pages = (int)v2_pages; P.pgstack = (int*)c->d_pgstack.p;
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)(pl.n_cl * C));
       cfg.blockDim = dim3((unsigned)threads);
@@ -666,7 +693,9 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       if (pl.v2) {
         if (threads == 128) CU(cudaLaunchKernelEx(&cfg, k2v2_align<128, 1>, P));
         else if (threads == 256) CU(cudaLaunchKernelEx(&cfg, k2v2_align<256, 2>, P));
+        else if (threads == 320) CU(cudaLaunchKernelEx(&cfg, k2v2_align<320, 2>, P));
         else if (threads == 512) CU(cudaLaunchKernelEx(&cfg, k2v2_align<512, 1>, P));
+        else if (big_minb >= 2) CU(cudaLaunchKernelEx(&cfg, k2v2_align<384, 2>, P));
         else CU(cudaLaunchKernelEx(&cfg, k2v2_align<384, 1>, P));
       } else if (a.metric == 1) {
         if (pl.wide) CU(cudaLaunchKernelEx(&cfg, k2_align<true, int32_t>, P)); else CU(cudaLaunchKernelEx(&cfg, k2_align<true, int16_t>, P));
@@ -698,7 +727,29 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       size_t need = 0;
       for (size_t j = 0; j < jobs.size(); ++j) need += plans[j].slab * plans[j].n_cl;
       if ((rc = ensure(c, c->d_ws, need))) return rc;
+      // the page pool of the v2 jobs: what they wish for, at least two pages per resident pair, at most what is left
+      size_t wish = 0, resident = 0;
+      for (size_t j = 0; j < jobs.size(); ++j)
+        if (plans[j].v2) { wish += plans[j].rows_want * plans[j].n_cl; resident += plans[j].n_cl; }
+      if (resident) {
+        const size_t left = avail > need ? avail - need : 0;
+        size_t bytes = std::min(std::max(wish, (resident * 3 + 8) << kPageShift), left);
+        v2_pages = std::min(bytes >> kPageShift, kMaxPages);
+        if (v2_pages < 4) return fail(c, SFC_ERR_OOM, "device workspace too small for the wavefront page pool");
+        if ((rc = ensure(c, c->d_pages, v2_pages << kPageShift))) return rc;
+        v2_pages = std::min(v2_pages, c->d_pages.cap >> kPageShift);
+        if ((rc = ensure(c, c->d_pgstack, (kMaxPages + 2) * 4))) return rc;
+      }
     }
+    auto reset_pool = [&]() -> int {  // every page free (stream-ordered before the launches of a pass)
+      if (!v2_pages) return 0;
+      c->h_pgstack.resize(v2_pages + 2);
+      c->h_pgstack[0] = 0; c->h_pgstack[1] = (int)v2_pages;
+      for (size_t i = 0; i < v2_pages; ++i) c->h_pgstack[2 + i] = (int)(v2_pages - 1 - i);
+      CU(cudaMemcpyAsync(c->d_pgstack.p, c->h_pgstack.data(), (v2_pages + 2) * 4, cudaMemcpyHostToDevice, c->stream));
+      return 0;
+    };
+    if ((rc = reset_pool())) return rc;
     CU(cudaMemsetAsync(misc + 8, 0, 32, c->stream));
     {
       // rewrite the K2 part of the order array job by job
@@ -764,11 +815,15 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       if (force_c_env > 0) Cr = force_c_env;
       if ((rc = plan_job(retry, big_threads, Cr, avail, divisor, &pl))) return rc;
       if ((rc = ensure(c, c->d_ws, pl.slab * pl.n_cl))) return rc;
+      if (pl.v2) {
+        if (!v2_pages) return fail(c, SFC_ERR_CUDA, "internal: retry pass without a page pool");
+        if ((rc = reset_pool())) return rc;
+      }
       cur = retry;
       CU(cudaMemcpyAsync((uint32_t*)c->d_order.p + k2s_begin, retry.data(), retry.size() * 4, cudaMemcpyHostToDevice, c->stream));
       CU(cudaMemsetAsync(misc + 8, 0, 4, c->stream));
       if ((rc = launch_job((const uint32_t*)c->d_order.p + k2s_begin, retry.size(), big_threads, Cr, pl, (unsigned char*)c->d_ws.p, misc + 8, c->stream))) return rc;
-      if (pl.n_cl == 1 && pl.slab >= avail - 4096 && !pool_short) divisor = 1 << 20;  // last resort was tried
+      if (pl.n_cl == 1 && (pl.v2 || pl.slab >= avail - 4096) && !pool_short) divisor = 1 << 20;  // last resort was tried
     }
   }
   CU(cudaEventRecord(c->ev[4], c->stream));
@@ -1014,6 +1069,8 @@ extern "C" int sfc_aligner_align(sfc_aligner* a, const uint8_t* pattern, size_t 
   if (rc) return rc;
   if (status != 0)  // per-pair status -> sfc_error: only -5 / -6 share their meaning with the error enum
     return fail(c, (status == SFC_STATUS_UNSUPPORTED || status == SFC_STATUS_OOM) ? status : SFC_ERR_INTERNAL, "align: pair status %d", status);
+  a->last_ops.assign(ops.begin(), ops.begin() + (size_t)off[1]);
+  a->last_pattern.assign(pattern, pattern + len);
   int hm = 0;
   size_t nc = 0;
   int64_t roff = 0;
@@ -1022,6 +1079,30 @@ extern "C" int sfc_aligner_align(sfc_aligner* a, const uint8_t* pattern, size_t 
   if (has_alignment) *has_alignment = hm;
   if (ref_offset) *ref_offset = roff;
   if (n_cigar) *n_cigar = nc;
+  return SFC_OK;
+}
+
+// Debug view of the last alignment (reference src/wfa2_utils.rs:253-255: PairwiseAligner::matching -> WFAligner::matching):
+// the gapped pattern, a line of '|' under matches, the gapped text, in the order the sequences were aligned (reversed).
+extern "C" int sfc_aligner_matching(sfc_aligner* a, char* pattern_line, char* mid_line, char* text_line, size_t cap, size_t* out_len) {
+  if (!a || !out_len) return SFC_ERR_INVALID;
+  size_t n = 0;
+  for (uint32_t w : a->last_ops) n += w >> 2;
+  *out_len = n;
+  if (n == 0) return a->last_ops.empty() && a->last_pattern.empty() ? fail(a->ctx, SFC_ERR_INVALID, "matching: no alignment yet") : SFC_OK;
+  if (!pattern_line || !mid_line || !text_line || cap < n) return fail(a->ctx, SFC_ERR_CAPACITY, "matching: need %zu bytes per line", n);
+  const size_t pl = a->last_pattern.size(), tl = a->text.size();
+  size_t v = 0, h = 0, pos = 0;  // positions in the REVERSED pattern / text
+  for (uint32_t w : a->last_ops) {
+    const uint32_t code = w & 3u;
+    for (uint32_t i = 0; i < (w >> 2); ++i, ++pos) {
+      const char pc = (code != SFC_OP_I && v < pl) ? (char)a->last_pattern[pl - 1 - v] : '-';
+      const char tc = (code != SFC_OP_D && h < tl) ? (char)a->text[tl - 1 - h] : '-';
+      pattern_line[pos] = pc; text_line[pos] = tc; mid_line[pos] = code == SFC_OP_M ? '|' : ' ';
+      if (code != SFC_OP_I) ++v;
+      if (code != SFC_OP_D) ++h;
+    }
+  }
   return SFC_OK;
 }
 

@@ -103,3 +103,53 @@ class PairwiseAligner:
 
     def align_end_to_end(self, pattern: bytes):
         return self._align(pattern, 2)
+
+    def matching(self, text: bytes = b"", pattern: bytes = b"") -> Tuple[str, str, str]:
+        """Debug view of the last alignment (src/wfa2_utils.rs:253-255): gapped pattern, '|' under matches, gapped text,
+        in the order the sequences were aligned (both reversed).  The arguments are accepted for signature parity; like
+        WFA2's `matching` the lines come from the aligner's stored cigar."""
+        L = _lib.lib()
+        n = C.c_size_t()
+        rc = L.sfc_aligner_matching(self._h, None, None, None, 0, C.byref(n))
+        if n.value == 0:
+            if rc not in (0, -4):
+                raise SfcError(rc, "matching: no alignment yet")
+            return "", "", ""
+        bufs = [C.create_string_buffer(n.value) for _ in range(3)]
+        rc = L.sfc_aligner_matching(self._h, bufs[0], bufs[1], bufs[2], n.value, C.byref(n))
+        if rc != 0:
+            raise SfcError(rc, "matching")
+        return tuple(b.raw[:n.value].decode() for b in bufs)
+
+
+def get_pairwise_alignment_mismatch_line(lines, start: int, end: int) -> str:
+    """src/utils.rs:139-166: '|' match, 'X' mismatch, ' ' gap between the first two lines."""
+    out = []
+    for pos in range(start, end):
+        a, b = lines[0][pos:pos + 1], lines[1][pos:pos + 1]
+        out.append(" " if a == b"-" or b == b"-" else ("|" if a == b else "X"))
+    return "".join(out)
+
+
+def pairwise_alignment_printer(width: int, lines, file=None) -> None:
+    """src/utils.rs:174-213: wraps a pairwise alignment over rows of `width` columns with a ruler and a mismatch line."""
+    import sys
+    file = file or sys.stderr
+    assert len(lines) > 1
+    n = len(lines[0])
+    assert len(lines[1]) == n
+    ruler = "".join("." if (i + 1) % 10 == 0 else " " for i in range(width))
+    for row in range((n + width - 1) // width):
+        start, end = width * row, min(width * row + width, n)
+        print(ruler, file=file)
+        print(bytes(lines[0][start:end]).decode(), file=file)
+        print(get_pairwise_alignment_mismatch_line(lines, start, end), file=file)
+        print(bytes(lines[1][start:end]).decode(), file=file)
+        print(file=file)
+
+
+def print_pairwise_alignment(aligner: "PairwiseAligner", pattern: bytes, file=None) -> None:
+    """src/wfa2_utils.rs:258-273: text over pattern, in forward orientation, 150 columns per row."""
+    l1, _, l3 = aligner.matching(aligner.text(), bytes(pattern)[::-1])
+    pairwise_alignment_printer(150, [l3.encode()[::-1], l1.encode()[::-1]], file=file)
+

@@ -258,3 +258,24 @@ def test_arena_may_be_reused_as_soon_as_upload_returns(ctx, oracle):
         ctx.run(lin, False)
         got, st, _, _ = ctx.download()
         assert (st == 0).all() and (got == want).all()
+
+
+def test_matching_debug_view(ctx):
+    """PairwiseAligner::matching / print_pairwise_alignment (reference src/wfa2_utils.rs:253-273): the three display lines
+    of the last alignment spell out both (reversed) sequences and mark exactly the matching columns."""
+    import io
+    from sawfish_b200.wfa2_utils import PairwiseAligner, print_pairwise_alignment
+    al = PairwiseAligner.new_consensus_aligner(ctx)
+    text, pat = b"AACTGTATAA", b"ACTTAT"
+    al.set_text(text)
+    al.align(pat)
+    l1, l2, l3 = al.matching(al.text(), pat[::-1])
+    assert len(l1) == len(l2) == len(l3)
+    assert l1.replace("-", "").encode() == pat[::-1] and l3.replace("-", "").encode() == text[::-1]
+    for a, m, b in zip(l1, l2, l3):
+        assert (m == "|") == (a == b and a != "-")
+    assert l2.count("|") == 6
+    out = io.StringIO()
+    print_pairwise_alignment(al, pat, file=out)
+    rows = out.getvalue().splitlines()
+    assert rows[1].replace("-", "").encode() == text and rows[3].replace("-", "").encode() == pat and "|" in rows[2]
