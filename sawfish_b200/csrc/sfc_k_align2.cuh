@@ -610,8 +610,39 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
       }
       V2_TICK(t_sync);
       // ---- trims (see k2_align): scans that crossed a long out-of-matrix run at the previous score are done by all warps ----
+      // warp 0's narrow probes (the first three diagonals of every scan that was short at the previous score) are issued
+      // first so that their round trip overlaps the cooperative wide scans below
+      const int tr_t = lane / 3, tr_j = lane - 3 * tr_t, tr_c = min(tr_t >> 1, 4), tr_side = tr_t & 1;
+      int tr_v = V2_NULL, tr_clo = 1, tr_chi = -1, tr_q = 0, tr_k = 0, tr_wprev = 0;
+      bool tr_en = false, tr_wide = false, tr_ok = false;
+      if (warp == 0) {
+        tr_en = tr_t < 2 * ncomp && (tr_c == K2_C_M || s > 0) && !((tr_c == K2_C_I2 || tr_c == K2_C_D2) && !has2);
+        tr_clo = tr_en ? misc[V2_CLO + tr_c] : 1; tr_chi = tr_en ? misc[V2_CHI + tr_c] : -1;
+        tr_q = misc[V2_Q + 7 + tr_c];
+        tr_k = tr_side ? tr_chi - tr_j : tr_clo + tr_j;
+        tr_wprev = (tr_t < 10 && anyw_s) ? misc[V2_WIDE + tr_t] : 0;
+        tr_wide = tr_en && tr_wprev > 3;
+        tr_ok = !tr_wide && tr_k >= tr_clo && tr_k <= tr_chi;
+        tr_v = tr_ok ? rd(tr_q, tr_k) : V2_NULL;
+      }
       if (anyw_s) {
-        for (int t = 0; t < 2 * ncomp; ++t) {
+        // first block (32 diagonals per warp) of every wide scan: all loads in flight together
+        int pv0[10];
+#pragma unroll
+        for (int t = 0; t < 10; ++t) {
+          pv0[t] = V2_NULL;
+          const int w = misc[V2_WIDE + t];
+          const int c = t >> 1, side = t & 1;
+          if (w > 3 && (c == K2_C_M || s > 0) && !((c == K2_C_I2 || c == K2_C_D2) && !has2)) {
+            const int clo = misc[V2_CLO + c], chi = misc[V2_CHI + c];
+            const int win_n = min(w + 64, chi - clo + 1);
+            const int per = min((win_n + NW * 32 - 1) / (NW * 32), 8);
+            const int off = warp * per * 32 + lane;
+            if (off < win_n) pv0[t] = rd(misc[V2_Q + 7 + c], side ? chi - off : clo + off);
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 10; ++t) {
           const int w = misc[V2_WIDE + t];
           if (w <= 3) continue;
           const int c = t >> 1, side = t & 1;
@@ -621,21 +652,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
           const int win_n = min(w + 64, chi - clo + 1);
           const int per = min((win_n + NW * 32 - 1) / (NW * 32), 8);
           const int o = warp * per * 32;
-          int pv8[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int off = o + 32 * u + lane;
-            const int kk = side ? chi - off : clo + off;
-            pv8[u] = (u < per && off < win_n) ? rd(q, kk) : V2_NULL;
-          }
           bool got = false;
           int pos = 0;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < per; ++u) {  // per is 1 unless the run is longer than the CTA is wide
             const int off = o + 32 * u + lane;
             const int kk = side ? chi - off : clo + off;
-            const unsigned b = __ballot_sync(FULL, u < per && off < win_n && in_mat(pv8[u], kk));
-            if (b && !got) { got = true; const int fo = o + 32 * u + __ffs((int)b) - 1; pos = side ? chi - fo : clo + fo; }
+            const int pv = u == 0 ? pv0[t] : (off < win_n ? rd(q, kk) : V2_NULL);
+            const unsigned b = __ballot_sync(FULL, off < win_n && in_mat(pv, kk));
+            if (b) { got = true; const int fo = o + 32 * u + __ffs((int)b) - 1; pos = side ? chi - fo : clo + fo; break; }
           }
           if (got && lane == 0) { if (side) atomicMax(misc + V2_CAND + t, pos); else atomicMin(misc + V2_CAND + t, pos); }
         }
@@ -643,15 +667,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
       }
       if (warp == 0) {
         {
-          const int t = lane / 3, j = lane - 3 * t, c = min(t >> 1, 4), side = t & 1;
-          const bool en = t < 2 * ncomp && (c == K2_C_M || s > 0) && !((c == K2_C_I2 || c == K2_C_D2) && !has2);
-          const int clo = en ? misc[V2_CLO + c] : 1, chi = en ? misc[V2_CHI + c] : -1;
-          const int q = misc[V2_Q + 7 + c];
-          const int k = side ? chi - j : clo + j;
-          const int wprev = (t < 10 && anyw_s) ? misc[V2_WIDE + t] : 0;
-          const bool wide = en && wprev > 3;
-          const bool ok = !wide && k >= clo && k <= chi;
-          const int v = ok ? rd(q, k) : V2_NULL;
+          const int t = tr_t, j = tr_j, c = tr_c, side = tr_side;
+          const bool en = tr_en, wide = tr_wide, ok = tr_ok;
+          const int clo = tr_clo, chi = tr_chi, q = tr_q, k = tr_k, wprev = tr_wprev, v = tr_v;
           const unsigned hits = __ballot_sync(FULL, ok && in_mat(v, k));
           const unsigned mine = (hits >> (3 * t)) & 7u;
           int found = side ? -1 : 1;

@@ -474,7 +474,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     const int nG1 = a.e1 + 1, nG2 = a.e2 + 1;
     const int nslots = a.metric == 1 ? nM + 2 * nG1 + 2 * nG2 : nM;
 
-    struct Job { std::vector<uint32_t> list; int threads; int C; double max_est = 0; };
+    struct Job { std::vector<uint32_t> list; int threads; int C; double max_est = 0; bool small_job = false; };
     auto kernel_of = [&](bool wide) -> const void* {
       if (a.metric == 1) return wide ? (const void*)k2_align<true, int32_t> : (const void*)k2_align<true, int16_t>;
       return wide ? (const void*)k2_align<false, int32_t> : (const void*)k2_align<false, int16_t>;
@@ -482,7 +482,9 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     // K2 v2 launch shapes (sfc_k_align2.cuh): 128 threads for small pairs; for the rest SFC_K2_SHAPE = "threads[,CTAs per SM]"
     // picks one of the compiled (threads, CTAs / SM) variants (default 384 x 1)
     auto v2_kernel = [&](int threads, int minb) -> const void* {
-      if (threads == 128) return (const void*)k2v2_align<128, 1>;
+      if (threads == 128 && minb < 2) return (const void*)k2v2_align<128, 1>;
+      if (threads == 160) return (const void*)k2v2_align<160, 3>;
+      if (threads == 128 && minb >= 2) return (const void*)k2v2_align<128, 4>;
       if (threads == 256) return (const void*)k2v2_align<256, 2>;
       if (threads == 320) return (const void*)k2v2_align<320, 2>;
       if (threads == 512) return (const void*)k2v2_align<512, 1>;
@@ -491,18 +493,21 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     };
     int big_threads = K2_LB_T, big_minb = 1;
     if (a.metric == 1 && !getenv("SFC_K2_V1")) {
+      // default: two 256-thread CTAs per SM — one pair's serial trim / plan section and its barrier waits overlap the other
+      // pair's cell phase (config2 77 vs 83 ms, config3 70 vs 74 ms against one 384-thread CTA per SM)
+      big_threads = 256; big_minb = 2;
       if (const char* e = getenv("SFC_K2_SHAPE")) {
         int t = 0, b = 0;
         const int got = sscanf(e, "%d,%d", &t, &b);
-        if (got >= 1 && (t == 256 || t == 320 || t == 384 || t == 512)) {
+        if (got >= 1 && (t == 128 || t == 160 || t == 256 || t == 320 || t == 384 || t == 512)) {
           big_threads = t;
-          big_minb = (t == 256 || t == 320) ? 2 : (t == 384 && got >= 2 && b >= 2) ? 2 : 1;
+          big_minb = t == 128 ? 4 : t == 160 ? 3 : (t == 256 || t == 320) ? 2 : (t == 384 && got >= 2 && b >= 2) ? 2 : 1;
         }
       }
     }
     std::vector<Job> jobs;
     // small pairs: one 128-thread CTA each
-    if (k2l_begin > k2s_begin) jobs.push_back(Job{std::vector<uint32_t>(c->h_order.begin() + k2s_begin, c->h_order.begin() + k2l_begin), 128, 1});
+    if (k2l_begin > k2s_begin) jobs.push_back(Job{std::vector<uint32_t>(c->h_order.begin() + k2s_begin, c->h_order.begin() + k2l_begin), 128, 1, 0, true});
     // large pairs: 384-thread CTAs; a pair whose estimated work exceeds the balanced per-SM share is spread over a
     // thread-block cluster of 2/4/8 CTAs so that the heaviest alignment does not set the batch time
     if (n > k2l_begin) {
@@ -516,14 +521,14 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       }
       int force_c = 0;
       if (const char* e = getenv("SFC_K2_CLUSTER")) force_c = atoi(e);
-      double share = std::max(total / (double)c->sm_count, 2e6);
-      if (a.metric == 1 && !getenv("SFC_K2_V1")) {
-        // K2 v2 keeps 10 B of wavefront history per cell (budgeted at 1.5 x the estimate): a pair whose history does not
-        // fit one resident CTA's share of device memory is spread over a cluster, whose slab is that many shares
-        const int occ_guess = big_minb;
-        const double mem_share = (double)avail * 0.80 / ((double)c->sm_count * occ_guess) / 15.0;
-        share = std::min(share, std::max(mem_share, 2e6));
-      }
+      // a pair heavier than the balanced share of one resident CTA is spread over a cluster (K2 v2 may keep several CTAs
+      // per SM: each then has a fraction of the SM's throughput)
+      const int occ_guess = (a.metric == 1 && !getenv("SFC_K2_V1")) ? big_minb : 1;
+      // (measured on config2 / config3, profiles/r02_k2v2_shape_sweep.md: cutting finer than the balanced share costs more
+      // in cluster barriers than it saves in tail)
+      double share_div = 1.0;
+      if (const char* e = getenv("SFC_K2_SHARE_DIV")) share_div = std::max(0.25, atof(e));  // experiment knob
+      const double share = std::max(total / ((double)c->sm_count * occ_guess * share_div), 2e6);
       std::vector<uint32_t> byc[4];
       std::vector<std::pair<double, uint32_t>> tmp[4];
       for (size_t q = 0; q < nl; ++q) {
@@ -545,14 +550,14 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     }
 
     // size one job's launch: returns grid (in clusters), slab bytes, shared bytes, win_cap
-    struct Plan { size_t n_cl, slab, smem, max_fixed, rows_want; int win_cap, stages; bool wide; bool v2; };
+    struct Plan { size_t n_cl, slab, smem, max_fixed, rows_want; int win_cap, stages, minb; bool wide; bool v2; };
     constexpr int kPageShift = 23;          // 8 MB pages
     constexpr size_t kMaxPages = 15360;     // 120 GB: row origins are 32-bit counts of 64-byte units
     size_t v2_pages = 0;                    // pages of the pool of this run (0: no v2 job)
     // max_est: estimated wavefront cells of the heaviest pair of the list (0 = unknown).  One choice byte is kept per cell,
     // so the slab's choice-byte budget follows it: a pair that runs out is re-run from scratch in an escalation pass, at
     // the tail of the batch, which costs far more than the memory does (180 GB of HBM).
-    auto plan_job = [&](const std::vector<uint32_t>& list, int threads, int C, size_t budget, int divisor, Plan* pl, double max_est = 0) -> int {
+    auto plan_job = [&](const std::vector<uint32_t>& list, int threads, int C, size_t budget, int divisor, Plan* pl, double max_est = 0, bool small_job = false) -> int {
       size_t max_fixed = 0, max_win = 0, max_W = 0;
       bool wide = false;
       for (uint32_t pi : list) wide = wide || c->h_pairs[pi].plen > K2_MAX_LEN16 || c->h_pairs[pi].tlen > K2_MAX_LEN16;
@@ -589,11 +594,12 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
         int st2 = 2;
         if (const char* e = getenv("SFC_K2_STAGES")) st2 = std::max(1, std::min(3, atoi(e)));
         // shared memory per CTA such that the variant's CTAs per SM all fit (228 KB per SM, 1 KB reserved per CTA)
-        const int minb = threads == 128 ? 1 : big_minb;
+        const int minb = small_job ? 1 : big_minb;
         const size_t sm_cap = std::min<size_t>(c->smem_optin, ((size_t)228 * 1024) / (size_t)minb - 1024);
         while (st2 > 1 && fixed_sm2 + st2 * per_stage2 > sm_cap) --st2;
         if (fits && fixed_sm2 + st2 * per_stage2 <= c->smem_optin) {
           pl->v2 = true;
+          pl->minb = minb;
           pl->wide = false;
           pl->win_cap = (int)max_win;
           pl->stages = st2;
@@ -691,11 +697,13 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       if (pl.v2) {
-        if (threads == 128) CU(cudaLaunchKernelEx(&cfg, k2v2_align<128, 1>, P));
+        if (threads == 128 && pl.minb < 2) CU(cudaLaunchKernelEx(&cfg, k2v2_align<128, 1>, P));
+        else if (threads == 128) CU(cudaLaunchKernelEx(&cfg, k2v2_align<128, 4>, P));
+        else if (threads == 160) CU(cudaLaunchKernelEx(&cfg, k2v2_align<160, 3>, P));
         else if (threads == 256) CU(cudaLaunchKernelEx(&cfg, k2v2_align<256, 2>, P));
         else if (threads == 320) CU(cudaLaunchKernelEx(&cfg, k2v2_align<320, 2>, P));
         else if (threads == 512) CU(cudaLaunchKernelEx(&cfg, k2v2_align<512, 1>, P));
-        else if (big_minb >= 2) CU(cudaLaunchKernelEx(&cfg, k2v2_align<384, 2>, P));
+        else if (pl.minb >= 2) CU(cudaLaunchKernelEx(&cfg, k2v2_align<384, 2>, P));
         else CU(cudaLaunchKernelEx(&cfg, k2v2_align<384, 1>, P));
       } else if (a.metric == 1) {
         if (pl.wide) CU(cudaLaunchKernelEx(&cfg, k2_align<true, int32_t>, P)); else CU(cudaLaunchKernelEx(&cfg, k2_align<true, int16_t>, P));
@@ -714,14 +722,14 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       size_t demand_total = 0;
       std::vector<size_t> demand(jobs.size());
       for (size_t j = 0; j < jobs.size(); ++j) {
-        if ((rc = plan_job(jobs[j].list, jobs[j].threads, jobs[j].C, avail, 1, &plans[j], jobs[j].max_est))) return rc;
+        if ((rc = plan_job(jobs[j].list, jobs[j].threads, jobs[j].C, avail, 1, &plans[j], jobs[j].max_est, jobs[j].small_job))) return rc;
         demand[j] = plans[j].slab * plans[j].n_cl;
         demand_total += demand[j];
       }
       if (demand_total > avail) {
         for (size_t j = 0; j < jobs.size(); ++j) {
           const size_t budget = std::max<size_t>((size_t)((double)avail * ((double)demand[j] / (double)demand_total)), plans[j].max_fixed + (1 << 20));
-          if ((rc = plan_job(jobs[j].list, jobs[j].threads, jobs[j].C, budget, 1, &plans[j], jobs[j].max_est))) return rc;
+          if ((rc = plan_job(jobs[j].list, jobs[j].threads, jobs[j].C, budget, 1, &plans[j], jobs[j].max_est, jobs[j].small_job))) return rc;
         }
       }
       size_t need = 0;
@@ -739,6 +747,16 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
         if ((rc = ensure(c, c->d_pages, v2_pages << kPageShift))) return rc;
         v2_pages = std::min(v2_pages, c->d_pages.cap >> kPageShift);
         if ((rc = ensure(c, c->d_pgstack, (kMaxPages + 2) * 4))) return rc;
+        // more wished for than the pool holds: fewer pairs resident (a pair that finds the pool empty is re-run from
+        // scratch in an escalation pass, which costs far more than a shorter queue).  The wish already carries a 1.5 x
+        // margin and the resident pairs are never all at their largest at once (measured on config2: a wish of 1.7 x the
+        // pool runs without a single retry), so the queue only shrinks beyond 2 x.
+        const double have = (double)(v2_pages << kPageShift);
+        if ((double)wish > 2.0 * have) {
+          const double scale = 3.0 * have / (double)wish;
+          for (size_t j = 0; j < jobs.size(); ++j)
+            if (plans[j].v2 && scale < 1.0) plans[j].n_cl = std::max<size_t>(1, (size_t)((double)plans[j].n_cl * scale));
+        }
       }
     }
     auto reset_pool = [&]() -> int {  // every page free (stream-ordered before the launches of a pass)

@@ -75,3 +75,30 @@ def test_estimate_pair_work_monotone():
             (0, 0, 500, 500, 200, 200, 200, 200, 1)]
     w = estimate_pair_work(LARGE_INDEL_PENALTIES, np.array(rows, dtype=PAIR_DTYPE))
     assert w[1] > w[0] > w[2] > 0
+
+
+def test_bench_shard_cut_covers_every_pair_once_and_compacts_exactly():
+    """What bench.py does per rank at N > 1: the LPT plan over SV groups (identical on every rank), this rank's pairs, and a
+    compacted arena holding exactly their sequences — every pair lands on exactly one rank with its bytes unchanged."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from sawfish_b200.batch import LARGE_INDEL_PENALTIES
+    from sawfish_b200.sharding import shard_pairs
+    arena, pairs, groups = bench.make_batch("config2", 24, 11)
+    for world in (2, 4, 8):
+        seen = np.zeros(len(pairs), int)
+        for rank in range(world):
+            mine, plan = shard_pairs(LARGE_INDEL_PENALTIES, pairs, groups, world, rank)
+            seen[mine] += 1
+            assert len(np.unique(plan[groups[mine]])) <= 1          # whole groups only
+            la, lp = bench.compact_shard(arena, pairs, mine)
+            assert len(la) <= len(arena)
+            for i, j in enumerate(mine[:40]):
+                a, b = pairs[j], lp[i]
+                for off, ln in (("pattern_off", "pattern_len"), ("text_off", "text_len")):
+                    assert b[ln] == a[ln]
+                    assert (arena[int(a[off]):int(a[off]) + int(a[ln])] == la[int(b[off]):int(b[off]) + int(b[ln])]).all()
+        assert (seen == 1).all()
+    arena4, pairs4, groups4 = bench.make_batch("config4", 3, 5)
+    assert len(groups4) == len(pairs4) and groups4.max() == 2
