@@ -480,6 +480,7 @@ def run_leg(args, D, ctx, workload, reads, steps, warmup, cpu_budget, local_rank
         e2e_wall += time.perf_counter() - t0
         e2e_dev_ms += s["h2d_ms"] + s["pack_ms"] + s["kernel_ms"] + s["d2h_ms"]
         h2d_b += int(s["h2d_bytes"]); d2h_b += int(s["d2h_bytes"])
+        retries += s["retries"]
     clocks = sampler.stop() if sampler else None
     st = ctx.stats()
 
@@ -488,7 +489,7 @@ def run_leg(args, D, ctx, workload, reads, steps, warmup, cpu_budget, local_rank
     pairs_per_cycle = [float(len(glob[b][1])) for b in range(nb)]
     all_pairs = sum(pairs_per_cycle[it % nb] for it in range(steps))       # global pairs aligned in the timed steps
     all_cells_dp = sum(float(synth.gcups_cells(glob[it % nb][1])) for it in range(steps))
-    all_launches, all_cells, all_alg_bytes, all_retries = D.reduce([float(launches), float(cells), float(alg_bytes), float(retries)], "SUM")
+    all_launches, all_cells, all_alg_bytes, all_retries = D.reduce([float(launches), float(cells), float(alg_bytes), float(retries)], "SUM")  # retries: both legs
     (kern_ms_min,) = D.reduce([kern_ms], "MIN")
     if rank != 0:
         return None

@@ -70,7 +70,8 @@ struct K2Params {
   // K2 v2 (sfc_k_align2.cuh): the wavefront history of every resident pair lives in pages of one shared pool
   unsigned char* pages;  // n_pages pages of (1 << page_shift) bytes
   int page_shift, n_pages;
-  int* pgstack;         // [0] lock, [1] free pages, [2 ..] their ids
+  int* pgstack;         // [0] lock, [1] free pages, [2] pages reserved by the resident pairs, [4 ..] free page ids
+  const uint32_t* pair_pages;  // [pair index] pages the pair is expected to need (admission: see k2v2_align)
 };
 
 struct K2Range {

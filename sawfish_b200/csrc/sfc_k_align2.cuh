@@ -38,7 +38,7 @@ enum { V2_S = 4, V2_STATUS, V2_LO, V2_HI, V2_HAS2, V2_G1A, V2_G1B, V2_G2A, V2_G2
        V2_CLO = 65 /* 5 */, V2_CHI = 70 /* 5 */, V2_D64 = 76 /* two u64: units used, cells */, V2_TAB = 80 /* [32][5] */,
        V2_WIDE = 240 /* 10 */, V2_CAND = 250 /* 10 */, V2_PGSEQ = 260 /* 4: ring of this pair's page ids (rank 0's copy is read) */,
        V2_PGI = 264 /* index of the current page in that sequence */, V2_PGN = 265 /* pages acquired (rank 0) */, V2_NEED = 266 /* 64-byte units of this score's rows */,
-       V2_NUP = 267 /* 64-byte units per row (padded) */ };
+       V2_NUP = 267 /* 64-byte units per row (padded) */, V2_RSV = 268 /* pages reserved for the current pair (rank 0) */ };
 
 // ---- packed s16x2 helpers: DPX on the device, plain C++ on the host (tests/cpp/test_v2_recur.cu) ----
 #if defined(__CUDA_ARCH__)
@@ -133,7 +133,7 @@ __device__ __forceinline__ int v2_page_acquire(int* st) {  // -1: the pool is em
   volatile int* v = st;
   const int n = v[1];
   int id = -1;
-  if (n > 0) { id = v[1 + n]; v[1] = n - 1; }
+  if (n > 0) { id = v[3 + n]; v[1] = n - 1; }
   v2_pool_unlock(st);
   return id;
 }
@@ -142,7 +142,7 @@ __device__ __forceinline__ void v2_pages_release(int* st, const int* list, int c
   v2_pool_lock(st);
   volatile int* v = st;
   int n = v[1];
-  for (int i = 0; i < cnt; ++i) { const int id = list[i]; if (id >= 0) { v[2 + n] = id; ++n; } }
+  for (int i = 0; i < cnt; ++i) { const int id = list[i]; if (id >= 0) { v[4 + n] = id; ++n; } }
   v[1] = n;
   v2_pool_unlock(st);
 }
@@ -225,16 +225,29 @@ __global__ void __launch_bounds__(THREADS, MINB) k2v2_align(const K2Params P) {
   long long t_cells = 0, t_sync = 0, t_bt = 0, t_setup = 0, t_trim = 0, t_plan = 0, t_mark = clock64();
 #define V2_TICK(acc) do { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; } while (0)
 
-  if (tid == 0) misc[V2_PGN] = 0;
+  if (tid == 0) { misc[V2_PGN] = 0; misc[V2_RSV] = 0; }
   for (;;) {
     csync();
     V2_TICK(t_bt);
     if (crank == 0 && tid == 0) {
       int* pglist = reinterpret_cast<int*>(slab);
       v2_pages_release(P.pgstack, pglist, misc[V2_PGN]);  // the previous pair's history
-      misc[V2_PGN] = 0;
+      if (misc[V2_RSV] > 0) atomicSub(P.pgstack + 2, misc[V2_RSV]);
+      misc[V2_PGN] = 0; misc[V2_RSV] = 0;
       misc[0] = (int)atomicAdd(P.counter, 1u); misc[1] = misc[2] = INT_MAX;
-      if ((uint32_t)misc[0] < P.n) {  // the first two pages of the next pair (the second one is the reserve, see plan)
+      if ((uint32_t)misc[0] < P.n) {
+        // admission: the pair reserves the pages its work estimate says it will need and waits while the pool is
+        // promised to the pairs already resident (a pair that found the pool empty half-way would be re-run from scratch);
+        // a waiting pair holds nothing, and a pair alone on the device always starts
+        const int want = min((int)P.pair_pages[P.order[misc[0]]], P.n_pages);
+        for (;;) {
+          const int before = atomicAdd(P.pgstack + 2, want);
+          if (before == 0 || before + want <= P.n_pages) break;
+          atomicSub(P.pgstack + 2, want);
+          __nanosleep(2000);
+        }
+        misc[V2_RSV] = want;
+        // the first two pages of the pair (the second one is the reserve, see plan)
         const int p0 = v2_page_acquire(P.pgstack), p1 = v2_page_acquire(P.pgstack);
         pglist[0] = p0; pglist[1] = p1; misc[V2_PGN] = 2;
         misc[V2_PGSEQ] = p0; misc[V2_PGSEQ + 1] = p1; misc[V2_PGSEQ + 2] = misc[V2_PGSEQ + 3] = -1;

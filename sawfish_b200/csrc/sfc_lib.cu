@@ -53,7 +53,8 @@ struct sfc_ctx {
   size_t ws_limit = 0;
   // device buffers
   DevBuf d_arena, d_nib, d_seqs, d_seqwoff, d_pairs, d_order, d_scores, d_status, d_misc, d_pool, d_outoff, d_outlen, d_ws;
-  DevBuf d_pages, d_pgstack;  // K2 v2: the page pool of the wavefront history and its free stack
+  DevBuf d_pages, d_pgstack, d_pairpages;  // K2 v2: the page pool of the wavefront history, its free stack, pages expected per pair
+  std::vector<uint32_t> h_pairpages;
   std::vector<int> h_pgstack;
   DevBuf d_b_arena, d_b_pairs, d_b_out, d_b_pool;  // K4 (bio aligner) staging; the slabs reuse d_ws
   // batch state
@@ -251,7 +252,7 @@ extern "C" void sfc_destroy(sfc_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->d_arena, &c->d_nib, &c->d_seqs, &c->d_seqwoff, &c->d_pairs, &c->d_order, &c->d_scores, &c->d_status,
-                    &c->d_misc, &c->d_pool, &c->d_outoff, &c->d_outlen, &c->d_ws, &c->d_pages, &c->d_pgstack, &c->d_b_arena, &c->d_b_pairs, &c->d_b_out,
+                    &c->d_misc, &c->d_pool, &c->d_outoff, &c->d_outlen, &c->d_ws, &c->d_pages, &c->d_pgstack, &c->d_pairpages, &c->d_b_arena, &c->d_b_pairs, &c->d_b_out,
                     &c->d_b_pool})
     release(*b);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -685,7 +686,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       P.stages = pl.stages;
       P.max_score = INT_MAX / 4;
       P.prof = getenv("SFC_K2_PROF") ? (unsigned long long*)(misc + 40) : nullptr;
-      P.pages = (unsigned char*)c->d_pages.p; P.page_shift = kPageShift; P.n_pages = (int)v2_pages; P.pgstack = (int*)c->d_pgstack.p;
+      P.pages = (unsigned char*)c->d_pages.p; P.page_shift = kPageShift; P.n_pages = (int)v2_pages; P.pgstack = (int*)c->d_pgstack.p; P.pair_pages = (const uint32_t*)c->d_pairpages.p;
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)(pl.n_cl * C));
       cfg.blockDim = dim3((unsigned)threads);
@@ -714,6 +715,19 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       return 0;
     };
 
+    // The page pool of the K2 v2 jobs: what they wish for (never less than 2 GB when the device has it, nor than three pages
+    // per resident pair), at most what the device has left next to the slabs.  Grow-only across batches.
+    auto size_pool = [&](size_t wish, size_t resident, size_t slab_bytes) -> int {
+      const size_t left = avail > slab_bytes ? avail - slab_bytes : 0;
+      size_t bytes = std::max(std::max(wish, (size_t)2 << 30), (resident * 3 + 8) << kPageShift);
+      bytes = std::max(std::min(bytes, left), std::min<size_t>(c->d_pages.cap, left));
+      size_t pages = std::min(bytes >> kPageShift, kMaxPages);
+      if (pages < 4) return fail(c, SFC_ERR_OOM, "device workspace too small for the wavefront page pool");
+      int rc2 = ensure(c, c->d_pages, pages << kPageShift);
+      if (rc2) return rc2;
+      v2_pages = std::min(std::max(pages, c->d_pages.cap >> kPageShift), kMaxPages);
+      return ensure(c, c->d_pgstack, (kMaxPages + 4) * 4);
+    };
     // ---- first pass: all jobs back to back on the stream (heaviest clusters first) ----
     // Each job owns a slice of the workspace, of the order array and its own work counter.
     std::vector<Plan> plans(jobs.size());
@@ -740,13 +754,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       for (size_t j = 0; j < jobs.size(); ++j)
         if (plans[j].v2) { wish += plans[j].rows_want * plans[j].n_cl; resident += plans[j].n_cl; }
       if (resident) {
-        const size_t left = avail > need ? avail - need : 0;
-        size_t bytes = std::min(std::max(wish, (resident * 3 + 8) << kPageShift), left);
-        v2_pages = std::min(bytes >> kPageShift, kMaxPages);
-        if (v2_pages < 4) return fail(c, SFC_ERR_OOM, "device workspace too small for the wavefront page pool");
-        if ((rc = ensure(c, c->d_pages, v2_pages << kPageShift))) return rc;
-        v2_pages = std::min(v2_pages, c->d_pages.cap >> kPageShift);
-        if ((rc = ensure(c, c->d_pgstack, (kMaxPages + 2) * 4))) return rc;
+        if ((rc = size_pool(wish, resident, need))) return rc;
         // more wished for than the pool holds: fewer pairs resident (a pair that finds the pool empty is re-run from
         // scratch in an escalation pass, which costs far more than a shorter queue).  The wish already carries a 1.5 x
         // margin and the resident pairs are never all at their largest at once (measured on config2: a wish of 1.7 x the
@@ -761,10 +769,22 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     }
     auto reset_pool = [&]() -> int {  // every page free (stream-ordered before the launches of a pass)
       if (!v2_pages) return 0;
-      c->h_pgstack.resize(v2_pages + 2);
-      c->h_pgstack[0] = 0; c->h_pgstack[1] = (int)v2_pages;
-      for (size_t i = 0; i < v2_pages; ++i) c->h_pgstack[2 + i] = (int)(v2_pages - 1 - i);
-      CU(cudaMemcpyAsync(c->d_pgstack.p, c->h_pgstack.data(), (v2_pages + 2) * 4, cudaMemcpyHostToDevice, c->stream));
+      c->h_pgstack.resize(v2_pages + 4);
+      c->h_pgstack[0] = 0; c->h_pgstack[1] = (int)v2_pages; c->h_pgstack[2] = 0; c->h_pgstack[3] = 0;
+      for (size_t i = 0; i < v2_pages; ++i) c->h_pgstack[4 + i] = (int)(v2_pages - 1 - i);
+      CU(cudaMemcpyAsync(c->d_pgstack.p, c->h_pgstack.data(), (v2_pages + 4) * 4, cudaMemcpyHostToDevice, c->stream));
+      // pages each pair is expected to need: 10 B per wavefront cell at 1.4 x the work estimate (the estimate was at most
+      // 1.37 x short on the synthetic workloads), plus the two pages every pair holds from the start
+      c->h_pairpages.assign(n, 2);
+      for (size_t q = k2s_begin; q < n; ++q) {
+        const uint32_t pi = c->h_order[q];
+        const DevPair& d = c->h_pairs[pi];
+        const double cells = 1.4 * estimate_work(a, d.plen, d.tlen, d.pbf, d.tbf);
+        c->h_pairpages[pi] = (uint32_t)std::min<double>(cells * 10.0 / (double)((size_t)1 << kPageShift) + 3.0, (double)kMaxPages);
+      }
+      int rc3 = ensure(c, c->d_pairpages, n * 4);
+      if (rc3) return rc3;
+      CU(cudaMemcpyAsync(c->d_pairpages.p, c->h_pairpages.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
       return 0;
     };
     if ((rc = reset_pool())) return rc;
@@ -834,7 +854,9 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       if ((rc = plan_job(retry, big_threads, Cr, avail, divisor, &pl))) return rc;
       if ((rc = ensure(c, c->d_ws, pl.slab * pl.n_cl))) return rc;
       if (pl.v2) {
-        if (!v2_pages) return fail(c, SFC_ERR_CUDA, "internal: retry pass without a page pool");
+        // a pair ran out of pages: fewer pairs resident (divisor) AND a pool grown towards what the device has
+        const size_t prev = v2_pages;
+        if ((rc = size_pool(std::max(pl.rows_want * pl.n_cl, (prev << kPageShift) * 4), pl.n_cl, pl.slab * pl.n_cl))) return rc;
         if ((rc = reset_pool())) return rc;
       }
       cur = retry;
