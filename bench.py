@@ -98,10 +98,8 @@ def compact_shard(arena, pairs, idx):
     iv_end = np.maximum.reduceat(e, np.flatnonzero(new_iv))
     iv_len = iv_end - iv_start
     iv_new = np.concatenate([[0], np.cumsum(iv_len)[:-1]])
-    total = int(iv_len.sum())
-    # gather index: for every interval a contiguous range of source bytes
-    src = np.repeat(iv_start - iv_new, iv_len) + np.arange(total, dtype=np.int64)
-    local = arena[src]
+    # one slice copy per merged interval (an SV group's sequences are contiguous in the arena: ~ one interval per group)
+    local = np.concatenate([arena[a:b] for a, b in zip(iv_start.tolist(), iv_end.tolist())]) if len(iv_start) else np.zeros(0, np.uint8)
     which_p = np.searchsorted(iv_start, sub["pattern_off"].astype(np.int64), side="right") - 1
     which_t = np.searchsorted(iv_start, sub["text_off"].astype(np.int64), side="right") - 1
     sub["pattern_off"] = (sub["pattern_off"].astype(np.int64) - iv_start[which_p] + iv_new[which_p]).astype(np.uint64)

@@ -7,6 +7,7 @@
 
 #include "../../sawfish_b200/csrc/wfa2_utils.hpp"
 #include "../../sawfish_b200/csrc/score_sv_batch.hpp"
+#include "../../sawfish_b200/csrc/refine_sv_batch.hpp"
 
 using namespace sawfish_b200;
 
@@ -110,14 +111,82 @@ static int test_pair_batch_on_gpu(sfc_ctx* ctx) {
   return 0;
 }
 
+// refine_sv's two-region alt-haplotype text (src/refine_sv/align/mod.rs:708-793) and the speculative contig batch
+static int test_alt_hap_text_rules() {
+  const std::vector<uint8_t> s1 = {'A', 'A', 'A', 'A', 'C', 'C', 'C', 'C'}, s2 = {'G', 'G', 'T', 'T'};
+  auto str = [](const std::vector<uint8_t>& v) { return std::string(v.begin(), v.end()); };
+  AltHapSeq a = construct_alt_hap_seq(s1, s2, 3, false, true);
+  CHECK(str(a.seq) == "AAAACCCCNNNGGTT" && a.spacer_start == 8 && a.spacer_end == 11);
+  a = construct_alt_hap_seq(s1, s2, 3, false, false);
+  CHECK(str(a.seq) == "GGTTNNNAAAACCCC" && a.spacer_start == 4 && a.spacer_end == 7);
+  a = construct_alt_hap_seq(s1, s2, 3, true, true);
+  CHECK(str(a.seq) == "AAAACCCCNNNAACC");
+  CHECK(get_left_right_ref_flank_size(3500, false, true) == std::make_pair((int64_t)3500, (int64_t)2000));
+  CHECK(get_left_right_ref_flank_size(3500, true, true) == std::make_pair((int64_t)2000, (int64_t)3500));
+  CHECK(get_left_right_ref_flank_size(1500, true, false) == std::make_pair((int64_t)1500, (int64_t)1500));
+  CHECK(get_middle_flank_size(3500, false, true, 1100, 2100) == 500 && get_middle_flank_size(3500, true, true, 1100, 2100) == 3500);
+  return 0;
+}
+
+static int test_contig_batch_on_gpu(sfc_ctx* ctx) {
+  // two clusters; the first contig of cluster 0 is junk (no '=' anchors across the spacer), its retry contig is clean
+  const auto ref = lcg_seq(77u, 30000);
+  auto sub = [&](size_t a, size_t b) { return std::vector<uint8_t>(ref.begin() + a, ref.begin() + b); };
+  ContigBatch b;
+  std::vector<std::vector<size_t>> asm_pairs;
+  std::vector<AltHapSeq> texts;
+  for (int c = 0; c < 2; ++c) {
+    const size_t p1 = 6000 + 9000 * c, p2 = p1 + 4000;
+    texts.push_back(construct_alt_hap_seq(sub(p1 - 3500, p1 + 2000), sub(p2 - 2000, p2 + 3500), 100, false, true));
+    b.add_text(texts.back().seq.data(), texts.back().seq.size());
+    std::vector<size_t> pairs;
+    for (size_t flank : {1500u, 2500u}) {
+      std::vector<uint8_t> contig = sub(p1 - flank, p1);
+      const auto right = sub(p2, p2 + flank);
+      contig.insert(contig.end(), right.begin(), right.end());
+      if (c == 0 && flank == 1500) contig = lcg_seq(4242u, contig.size());
+      pairs.push_back(b.add_contig(contig.data(), contig.size()));
+    }
+    asm_pairs.push_back(pairs);
+  }
+  CHECK(b.align(ctx) == 0);
+  for (int c = 0; c < 2; ++c) {
+    const AltHapSeq& t = texts[(size_t)c];
+    auto crosses_spacer_with_deletion = [&](size_t, const SimpleAlignment& a) {
+      int64_t pos = a.ref_offset;
+      for (const auto& e : a.cigar) {
+        if (e.op == 'D' && pos <= t.spacer_start && pos + (int64_t)e.len >= t.spacer_end) return true;
+        if (e.op == 'D' || e.op == '=' || e.op == 'X') pos += e.len;
+      }
+      return false;
+    };
+    const auto k = b.first_passing(asm_pairs[(size_t)c], crosses_spacer_with_deletion);
+    CHECK(k.has_value() && *k == (c == 0 ? 1u : 0u));
+    // the batch equals the per-pair surface
+    auto al = PairwiseAligner::new_large_indel_aligner(ctx, false);
+    al.set_text(t.seq);
+    const size_t pi = asm_pairs[(size_t)c][*k];
+    std::vector<uint8_t> contig;  // rebuild the accepted contig
+    const size_t p1 = 6000 + 9000 * c, p2 = p1 + 4000, flank = *k == 0 ? 1500 : 2500;
+    contig = sub(p1 - flank, p1);
+    const auto right = sub(p2, p2 + flank);
+    contig.insert(contig.end(), right.begin(), right.end());
+    const auto one = al.align(contig);
+    CHECK(one.first == b.score(pi) && one.second.has_value() && one.second->ref_offset == b.alignment(pi)->ref_offset &&
+          one.second->cigar == b.alignment(pi)->cigar);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   const std::string mode = argc > 1 ? argv[1] : "host";
-  if (test_process_wfa2_cigar_string() || test_get_reverse() || test_pair_batch_geometry()) return 1;
+  if (test_process_wfa2_cigar_string() || test_get_reverse() || test_pair_batch_geometry() || test_alt_hap_text_rules()) return 1;
   if (mode == "gpu") {
     sfc_ctx* ctx = nullptr;
     if (sfc_create(0, &ctx) != 0) { std::cerr << "sfc_create failed: a B200 is required (no CPU fallback)\n"; return 2; }
     int rc = test_consensus_aligner(ctx);
     if (!rc) rc = test_pair_batch_on_gpu(ctx);
+    if (!rc) rc = test_contig_batch_on_gpu(ctx);
     sfc_destroy(ctx);
     if (rc) return rc;
   }

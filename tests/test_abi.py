@@ -121,3 +121,20 @@ def test_rust_crate_binds_only_declared_symbols_with_matching_arity():
     assert rs_fields("SfcPenalties") == c_fields("sfc_penalties")
     assert rs_fields("SfcPair") == c_fields("sfc_pair")
     assert rs_fields("SfcBioScoring") == c_fields("sfc_bio_scoring")
+
+
+def test_rust_patches_use_only_the_crate_surface():
+    """rust/sawfish-cuda/patches/*.rs (the two-phase score_sv / refine_sv batchers, source only) may use the crate's public
+    items only: no raw `sfc_*` FFI symbol, and every crate item they name exists in lib.rs."""
+    pdir = os.path.join(ROOT, "rust", "sawfish-cuda", "patches")
+    lib_rs = open(os.path.join(ROOT, "rust", "sawfish-cuda", "src", "lib.rs")).read()
+    files = sorted(f for f in os.listdir(pdir) if f.endswith(".rs"))
+    assert len(files) >= 2
+    for f in files:
+        src = re.sub(r"//[^\n]*", "", open(os.path.join(pdir, f)).read())
+        assert not re.findall(r"\bsfc_[a-z_]+\s*\(", src), f
+        for item in re.findall(r"use sawfish_cuda::\{([^}]*)\}", src):
+            for name in [x.strip() for x in item.split(",")]:
+                assert re.search(r"pub (struct|const|fn) " + name + r"\b", lib_rs), (f, name)
+        for meth in re.findall(r"ctx\.([a-z_]+)\(", src):
+            assert re.search(r"pub fn " + meth + r"\b", lib_rs), (f, meth)
