@@ -38,18 +38,18 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 WORKLOADS = {
     # name: preset, want_cigar, description, dominant kernel source (for the ncu traffic stamp)
-    "config2": dict(preset="large_indel", want_cigar=True, kernel="sfc_k_align.cuh",
+    "config2": dict(preset="large_indel", want_cigar=True, kernel="sfc_k_align2.cuh",
                     desc="configs[1]: read segments 2-20 kb x 2 allele haplotypes, 0.1% err, 35bp-5kb indel SV, gap-affine-2p + CIGAR"),
     "config2_linear": dict(preset="consensus", want_cigar=False, kernel="sfc_k_align.cuh",
                            desc="configs[1] inputs with the gap-linear consensus preset, score only"),
     "config2b": dict(preset="consensus", want_cigar=False, kernel="sfc_k_score.cuh",
                      desc="score_sv-shaped: 100-500 bp read flank x ref/alt allele flanks, gap-linear, score only"),
-    "config3": dict(preset="large_indel", want_cigar=True, kernel="sfc_k_align.cuh",
+    "config3": dict(preset="large_indel", want_cigar=True, kernel="sfc_k_align2.cuh",
                     desc="refine_sv-shaped: contig vs reference window (+2-region N spacer), gap-affine-2p + CIGAR"),
     "config4": dict(preset="consensus", want_cigar=False, kernel="sfc_k_score.cuh",
                     desc="configs[3] in miniature: 8-sample joint-call, per SV group x sample x read x breakend x registration x allele "
                          "flank pairs (100-500 bp, truncations, overlapping haplotypes), gap-linear, score only; --reads = SV groups per GPU"),
-    "config5": dict(preset="large_indel", want_cigar=True, kernel="sfc_k_align.cuh",
+    "config5": dict(preset="large_indel", want_cigar=True, kernel="sfc_k_align2.cuh",
                     desc="stress: 10-50 kb insertion/duplication haplotypes at 1-5% divergence"),
 }
 DEFAULT_READS = {"config4": 96, "config2": 1024, "config2_linear": 1024, "config2b": 200000, "config3": 512, "config5": 8}
