@@ -52,7 +52,7 @@ WORKLOADS = {
     "config5": dict(preset="large_indel", want_cigar=True, kernel="sfc_k_align2.cuh",
                     desc="stress: 10-50 kb insertion/duplication haplotypes at 1-5% divergence"),
 }
-DEFAULT_READS = {"config4": 96, "config2": 1024, "config2_linear": 1024, "config2b": 200000, "config3": 512, "config5": 8}
+DEFAULT_READS = {"config4": 96, "config2": 1024, "config2_linear": 1024, "config2b": 200000, "config3": 2048, "config5": 8}
 # secondary legs of the default line (N = 1): the score_sv shapes, i.e. K1 (smaller than their stand-alone defaults so
 # that the default run stays within minutes)
 SECONDARY = {"config2b": 100000, "config4": 64}
