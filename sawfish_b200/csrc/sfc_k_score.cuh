@@ -68,6 +68,28 @@ __device__ __forceinline__ bool k1_gsync_or(int, bool pred) {
   return __syncthreads_or(pred) != 0;
 }
 
+// count of leading zero bits; 0xFFFFFFFF for x == 0 (bfind.shiftamt = FLO.U32.SH, no fix-up for zero)
+__device__ __forceinline__ uint32_t k1_clz(uint32_t x) {
+  uint32_t d;
+  asm("bfind.shiftamt.u32 %0, %1;" : "=r"(d) : "r"(x));
+  return d;
+}
+
+// coop_extend (sfc_device.cuh) over the per-base windows
+__device__ __forceinline__ int k1_coop_extend(const uint32_t* __restrict__ wp, const uint32_t* __restrict__ wt, int plen, int tlen, int k, int h0, int lane) {
+  int adv = 0;
+  for (;;) {
+    const int h = h0 + adv + lane * 8, v = h - k;
+    uint32_t x = ~0u;
+    if (h <= tlen && v <= plen) x = wp[v] ^ wt[h];
+    const unsigned full = __ballot_sync(FULL, x == 0u);
+    if (full == FULL) { adv += 256; continue; }
+    const int first = __ffs((int)~full) - 1;
+    const int part = __shfl_sync(FULL, x ? (int)(k1_clz(x) >> 2) : 0, first);
+    return adv + first * 8 + part;
+  }
+}
+
 template <int WPP>
 __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
   extern __shared__ __align__(16) unsigned char k1_smem[];
@@ -75,9 +97,8 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
   const int group = threadIdx.x / G, g = threadIdx.x % G, lane = threadIdx.x & 31, gw = g >> 5;
   unsigned char* gs = k1_smem + (size_t)group * P.group_bytes;
   int32_t* ring = reinterpret_cast<int32_t*>(gs);
-  uint2* wp = reinterpret_cast<uint2*>(gs + (size_t)P.rd * P.wcap * 4);
-  uint2* wt = wp + P.win_cap;
-  int* meta = reinterpret_cast<int*>(wt + P.win_cap);  // [rd][2] lo,hi
+  uint32_t* wbase = reinterpret_cast<uint32_t*>(gs + (size_t)P.rd * P.wcap * 4);  // wcap words: both sequences' windows
+  int* meta = reinterpret_cast<int*>(wbase + P.wcap);  // [rd][2] lo,hi
   int* slot_pair = meta + 2 * P.rd;                     // [0] work index, [1] terminating diagonal
   const int rd = P.rd, wcap = P.wcap;
   unsigned long long cells_acc = 0;
@@ -90,12 +111,16 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
     const uint32_t pi = P.order[wi];
     const DevPair pr = P.pairs[pi];
     const int plen = pr.plen, tlen = pr.tlen;
+    // One 32-bit window PER BASE: wp[i] = the 8 bases from pattern position i (first base in the top nibble; positions
+    // past the end hold the end sentinel), so a cell's extension probe is two plain LDS.32, an XOR and a count of
+    // leading zeros.  wt[-1] (= the word after the pattern's last window) is what a null cell (offset -1) reads.
+    uint32_t* wp = wbase;
+    uint32_t* wt = wbase + plen + 2;
     {
-      const int nwp = (plen >> 3) + 1, nwt = (tlen >> 3) + 1;
       const uint32_t* gp = P.nib + pr.p_woff;
       const uint32_t* gt = P.nib + pr.t_woff;
-      for (int i = g; i < nwp; i += G) wp[i] = make_uint2(gp[i], gp[i + 1]);
-      for (int i = g; i < nwt; i += G) wt[i] = make_uint2(gt[i], gt[i + 1]);
+      for (int i = g; i <= plen; i += G) wp[i] = __brev(__funnelshift_r(gp[i >> 3], gp[(i >> 3) + 1], i << 2));
+      for (int i = g; i <= tlen; i += G) wt[i] = __brev(__funnelshift_r(gt[i >> 3], gt[(i >> 3) + 1], i << 2));
     }
     const int kbase = plen + 4;  // element index e = k + kbase >= 3 for every diagonal that is ever read
     k1_gsync<WPP>(group);
@@ -143,14 +168,13 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
             cell[j] = (k >= lo && k <= hi) ? ((max(k, 0) << 16) | (k + K1_K0BIAS)) : WNULL;
           }
         } else {
-          int4 a = make_int4(WNULL, WNULL, WNULL, WNULL), b = a;
-          int32_t bl = WNULL, br = WNULL;
-          if (gact) {
-            a = *reinterpret_cast<const int4*>(rowX + e0);
-            b = *reinterpret_cast<const int4*>(rowI + e0);
-            bl = rowI[e0 - 1];
-            br = rowI[e0 + 4];
-          }
+          // no guard for the lanes past the end of the wavefront: what they read lies inside this group's shared memory
+          // (the next ring row or the windows), their chunk is a boundary chunk (every element range-checked below),
+          // and they store nothing
+          int4 a = *reinterpret_cast<const int4*>(rowX + e0);
+          int4 b = *reinterpret_cast<const int4*>(rowI + e0);
+          int32_t bl = rowI[e0 - 1];
+          int32_t br = rowI[e0 + 4];
           const int kA = (gb << 2) - kbase;
           if (!(kA >= ilo && kA + 127 <= ihi)) {
             // boundary chunk: every element read is checked against its source row's live range — the four of the
@@ -176,6 +200,7 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
         // bounds + first 8-base window of the four cells (independent chains)
         uint32_t xw[4];
         int off[4];
+        const uint32_t* wpk = wp - k0;  // pattern position of (offset, diagonal k0 + j) = offset - k0 - j
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = k0 + j;
@@ -184,12 +209,12 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
           // no address guard for null cells (off = -1): pattern index -1 - k lies between -(tlen + 1) and plen - 1 and text
           // index -1 just below 0, i.e. inside this group's own shared memory (the ring precedes the pattern windows, the
           // pattern windows precede the text windows); what is loaded there is never used.
-          xw[j] = window8(wp, off[j] - k) ^ window8(wt, off[j]);
+          xw[j] = wpk[off[j] - j] ^ wt[off[j]];
         }
         int advmax = 0;  // 8 <=> some live cell matched its whole first window (lead_eq is at most 7)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int adv = (int)min(((unsigned)(__ffs((int)xw[j]) - 1)) >> 2, 8u);  // equal bases in the window; 8 when xw == 0 (ffs = 0)
+          const int adv = (int)min(k1_clz(xw[j]) >> 2, 8u);  // equal bases in the window; 8 when xw == 0 (bfind gives ~0)
           const int a = off[j] >= 0 ? adv : 0;
           off[j] += a;
           cell[j] += a << 16;  // the offset field moves with it (null cells: a = 0)
@@ -201,8 +226,8 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
             const int k = k0 + j;
             bool pending = false;
             if (off[j] >= 0 && xw[j] == 0u) {
-              const uint32_t x2 = window8(wp, off[j] - k) ^ window8(wt, off[j]);
-              if (x2) off[j] += lead_eq(x2);
+              const uint32_t x2 = wp[off[j] - k] ^ wt[off[j]];  // 8 real bases matched, so both positions are inside the sequences
+              if (x2) off[j] += (int)(k1_clz(x2) >> 2);
               else { off[j] += 8; pending = true; }
             }
             unsigned pm = __ballot_sync(FULL, pending);
@@ -210,7 +235,7 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
               const int src = __ffs((int)pm) - 1;
               pm &= pm - 1;
               const int ko = __shfl_sync(FULL, k, src), ho = __shfl_sync(FULL, off[j], src);
-              const int adv = coop_extend(wp, wt, plen, tlen, ko, ho, lane);
+              const int adv = k1_coop_extend(wp, wt, plen, tlen, ko, ho, lane);
               if (lane == src) off[j] += adv;
             }
             if (off[j] >= 0) cell[j] = (cell[j] & 0xFFFF) | (off[j] << 16);
