@@ -90,6 +90,13 @@ __device__ __forceinline__ int k1_coop_extend(const uint32_t* __restrict__ wp, c
   }
 }
 
+// Plan record of one score (written by the group's planner thread one score ahead, read by everybody after the barrier).
+// Without trimming the diagonal range of every wavefront follows from the ranges of its two source wavefronts alone,
+// never from cell values, so the planner runs ahead of the cells: no thread recomputes ranges, ring slots and row
+// addresses per score, and scores whose wavefront does not exist cost no barrier.
+enum { K1P_S = 0 /* score; -1: score cap reached */, K1P_LO, K1P_HI, K1P_ILO, K1P_IHI, K1P_LOX, K1P_CNTX, K1P_LOI, K1P_CNTI,
+       K1P_ROWX /* ring row offsets (cells) */, K1P_ROWI, K1P_ROWO, K1P_N };
+
 template <int WPP>
 __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
   extern __shared__ __align__(16) unsigned char k1_smem[];
@@ -98,9 +105,11 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
   unsigned char* gs = k1_smem + (size_t)group * P.group_bytes;
   int32_t* ring = reinterpret_cast<int32_t*>(gs);
   uint32_t* wbase = reinterpret_cast<uint32_t*>(gs + (size_t)P.rd * P.wcap * 4);  // wcap words: both sequences' windows
-  int* meta = reinterpret_cast<int*>(wbase + P.wcap);  // [rd][2] lo,hi
+  int* plan = reinterpret_cast<int*>(wbase + P.wcap);  // [2][K1P_N], double buffered by score iteration
+  int* meta = plan + 2 * K1P_N;                         // [rd][2] lo,hi of the wavefront in each ring slot (planner only)
   int* slot_pair = meta + 2 * P.rd;                     // [0] work index, [1] terminating diagonal
   const int rd = P.rd, wcap = P.wcap;
+  const bool planner = g == G - 32;  // lane 0 of the group's last warp (the warp with the fewest chunks)
   unsigned long long cells_acc = 0;
 
   for (;;) {
@@ -123,36 +132,50 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
       for (int i = g; i <= tlen; i += G) wt[i] = __brev(__funnelshift_r(gt[i >> 3], gt[(i >> 3) + 1], i << 2));
     }
     const int kbase = plen + 4;  // element index e = k + kbase >= 3 for every diagonal that is ever read
-    k1_gsync<WPP>(group);
 
-    int s = 0, res_status = 0, res_score = 0;
-    int slot_s = 0;  // s modulo rd, kept incrementally (an integer modulo by a run-time value costs ~25 instructions)
-    for (;; ++s, slot_s = (slot_s + 1 == rd ? 0 : slot_s + 1)) {
-      if (s > P.max_score) { res_status = -7; break; }
-      int lo, hi, lox = 1, hix = -1, loi = 1, hii = -1;
-      const int sx = s - P.x, si = s - P.ip;
-      const int slot_x = slot_s - P.x + (slot_s - P.x < 0 ? rd : 0), slot_i = slot_s - P.ip + (slot_s - P.ip < 0 ? rd : 0);
-      if (s == 0) {
-        lo = -pr.pbf; hi = pr.tbf;
-      } else {
+    // planner state: the last score planned and its ring slot (s modulo rd, kept incrementally)
+    int pl_s = 0, pl_slot = 0;
+    auto plan_next = [&](int* out) {
+      for (;;) {
+        ++pl_s; pl_slot = pl_slot + 1 == rd ? 0 : pl_slot + 1;
+        if (pl_s > P.max_score) { out[K1P_S] = -1; return; }
+        const int sx = pl_s - P.x, si = pl_s - P.ip;
+        const int slot_x = pl_slot - P.x + (pl_slot - P.x < 0 ? rd : 0), slot_i = pl_slot - P.ip + (pl_slot - P.ip < 0 ? rd : 0);
+        int lox = 1, hix = -1, loi = 1, hii = -1;
         if (sx >= 0) { lox = meta[2 * slot_x]; hix = meta[2 * slot_x + 1]; }
         if (si >= 0) { loi = meta[2 * slot_i]; hii = meta[2 * slot_i + 1]; }
         const bool hasx = lox <= hix, hasi = loi <= hii;
-        if (!hasx && !hasi) {  // wavefront s does not exist
-          if (g == 0) { meta[2 * slot_s] = 1; meta[2 * slot_s + 1] = -1; }
-          k1_gsync<WPP>(group);
-          continue;
-        }
+        if (!hasx && !hasi) { meta[2 * pl_slot] = 1; meta[2 * pl_slot + 1] = -1; continue; }  // wavefront does not exist
         // computed range, clamped to the diagonals of the matrix (cells outside are always null)
-        lo = max(min(hasx ? lox : INT_MAX, hasi ? loi - 1 : INT_MAX), -plen);
-        hi = min(max(hasx ? hix : INT_MIN, hasi ? hii + 1 : INT_MIN), tlen);
+        const int lo = max(min(hasx ? lox : INT_MAX, hasi ? loi - 1 : INT_MAX), -plen);
+        const int hi = min(max(hasx ? hix : INT_MIN, hasi ? hii + 1 : INT_MIN), tlen);
+        meta[2 * pl_slot] = lo; meta[2 * pl_slot + 1] = hi;
+        out[K1P_S] = pl_s; out[K1P_LO] = lo; out[K1P_HI] = hi;
+        out[K1P_ILO] = max(max(lox, loi + 1), lo); out[K1P_IHI] = min(min(hix, hii - 1), hi);  // every read in range, every cell active
+        out[K1P_LOX] = lox; out[K1P_CNTX] = max(hix - lox + 1, 0); out[K1P_LOI] = loi; out[K1P_CNTI] = max(hii - loi + 1, 0);
+        out[K1P_ROWX] = slot_x * wcap; out[K1P_ROWI] = slot_i * wcap; out[K1P_ROWO] = pl_slot * wcap;
+        return;
       }
-      if (g == 0) { meta[2 * slot_s] = lo; meta[2 * slot_s + 1] = hi; cells_acc += (unsigned long long)(hi - lo + 1); }
-      const int ilo = max(max(lox, loi + 1), lo), ihi = min(min(hix, hii - 1), hi);  // every read in range, every cell active
-      const int cntx = max(hix - lox + 1, 0), cnti = max(hii - loi + 1, 0);
-      const int32_t* rowX = ring + slot_x * wcap;
-      const int32_t* rowI = ring + slot_i * wcap;
-      int32_t* rowO = ring + slot_s * wcap;
+    };
+    if (planner) {  // score 0: the free-begin diagonals
+      int* out = plan;
+      meta[0] = -pr.pbf; meta[1] = pr.tbf;
+      out[K1P_S] = 0; out[K1P_LO] = -pr.pbf; out[K1P_HI] = pr.tbf; out[K1P_ILO] = 1; out[K1P_IHI] = 0;
+      out[K1P_LOX] = 1; out[K1P_CNTX] = 0; out[K1P_LOI] = 1; out[K1P_CNTI] = 0; out[K1P_ROWX] = 0; out[K1P_ROWI] = 0; out[K1P_ROWO] = 0;
+    }
+    k1_gsync<WPP>(group);
+
+    int s = 0, res_status = 0, res_score = 0;
+    for (int it = 0;; ++it) {
+      const int* pl = plan + (it & 1) * K1P_N;
+      const int4 q0 = *reinterpret_cast<const int4*>(pl), q1 = *reinterpret_cast<const int4*>(pl + 4), q2 = *reinterpret_cast<const int4*>(pl + 8);
+      s = q0.x;
+      if (s < 0) { res_status = -7; break; }
+      const int lo = q0.y, hi = q0.z, ilo = q0.w, ihi = q1.x, lox = q1.y, cntx = q1.z, loi = q1.w, cnti = q2.x;
+      const int32_t* rowX = ring + q2.y;
+      const int32_t* rowI = ring + q2.z;
+      int32_t* rowO = ring + q2.w;
+      if (planner) { cells_acc += (unsigned long long)(hi - lo + 1); plan_next(plan + ((it + 1) & 1) * K1P_N); }
       int term_k = INT_MAX;
       const int g_lo = (lo + kbase) >> 2, g_hi = (hi + kbase) >> 2;
 
@@ -200,7 +223,8 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
         // bounds + first 8-base window of the four cells (independent chains)
         uint32_t xw[4];
         int off[4];
-        const uint32_t* wpk = wp - k0;  // pattern position of (offset, diagonal k0 + j) = offset - k0 - j
+        const unsigned char* wpk = reinterpret_cast<const unsigned char*>(wp) - 4 * k0;  // pattern position of (offset, diagonal k0 + j) = offset - k0 - j
+        const unsigned char* wtb = reinterpret_cast<const unsigned char*>(wt);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = k0 + j;
@@ -208,16 +232,16 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
           if ((unsigned)off[j] > (unsigned)tlen || (unsigned)(off[j] - k) > (unsigned)plen) { cell[j] = WNULL; off[j] = -1; }
           // no address guard for null cells (off = -1): pattern index -1 - k lies between -(tlen + 1) and plen - 1 and text
           // index -1 just below 0, i.e. inside this group's own shared memory (the ring precedes the pattern windows, the
-          // pattern windows precede the text windows); what is loaded there is never used.
-          xw[j] = wpk[off[j] - j] ^ wt[off[j]];
+          // pattern windows precede the text windows); what is loaded there is made a mismatch by the sign of the offset.
+          const int ob = off[j] << 2;
+          xw[j] = (*reinterpret_cast<const uint32_t*>(wpk + ob - 4 * j) ^ *reinterpret_cast<const uint32_t*>(wtb + ob)) | (uint32_t)(off[j] >> 31);
         }
-        int advmax = 0;  // 8 <=> some live cell matched its whole first window (lead_eq is at most 7)
+        int advmax = 0;  // 8 <=> some live cell matched its whole first window
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int adv = (int)min(k1_clz(xw[j]) >> 2, 8u);  // equal bases in the window; 8 when xw == 0 (bfind gives ~0)
-          const int a = off[j] >= 0 ? adv : 0;
+          const int a = (int)min(k1_clz(xw[j]) >> 2, 8u);  // equal bases in the window; 8 when xw == 0 (bfind gives ~0); 0 for a null cell
           off[j] += a;
-          cell[j] += a << 16;  // the offset field moves with it (null cells: a = 0)
+          cell[j] += a << 16;  // the offset field moves with it
           advmax = max(advmax, a);
         }
         if (__any_sync(FULL, advmax == 8)) {  // rare: a run longer than 8 bases (the true diagonal)
@@ -254,7 +278,7 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
         }
         if (gact) *reinterpret_cast<int4*>(rowO + e0) = make_int4(cell[0], cell[1], cell[2], cell[3]);
       }
-      // ---- one barrier per score: rows complete + did any diagonal terminate ----
+      // ---- one barrier per score: rows and the next plan complete + did any diagonal terminate ----
       term_k = warp_min(term_k);
       if (term_k != INT_MAX && lane == 0) atomicMin(slot_pair + 1, term_k);
       if (k1_gsync_or<WPP>(group, term_k != INT_MAX)) {
@@ -270,7 +294,7 @@ __global__ void __launch_bounds__(256) k1_score(const K1Params P) {
     if (g == 0) { P.scores[pi] = res_score; P.status[pi] = res_status; }
     k1_gsync<WPP>(group);  // ring/windows are reused by the next pair
   }
-  if (g == 0 && cells_acc) atomicAdd(P.cells, cells_acc);
+  if (planner && cells_acc) atomicAdd(P.cells, cells_acc);
 }
 
 }  // namespace sfc

@@ -430,7 +430,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     P.win_cap = (wcap >> 3) + 4;
     P.max_score = INT_MAX / 4;
     P.cells = (unsigned long long*)(misc + 2);
-    size_t gb = (size_t)P.rd * wcap * 4 + (size_t)wcap * 4 /* per-base windows of both sequences */ + (size_t)(2 * P.rd + 2 * wpp * 3 + 2) * 4;
+    size_t gb = (size_t)P.rd * wcap * 4 + (size_t)wcap * 4 /* per-base windows of both sequences */ + (size_t)(2 * K1P_N + 2 * P.rd + 2) * 4;  // plan records, slot ranges, work index / terminating diagonal
     gb = (gb + 15) & ~(size_t)15;
     P.group_bytes = (int)gb;
     const size_t smem_max = c->smem_optin;
