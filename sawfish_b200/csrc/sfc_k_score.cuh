@@ -6,8 +6,11 @@
 // score is consumed (src/score_sv/mod.rs:702).
 //
 // Mapping: one group of WPP warps per pair, persistent groups pulling pairs from a global work counter.
-// The M-wavefront ring (depth max(x',i')+1) and both sequences (4-bit, overlapped 8-byte windows) live in
-// shared memory.  Each wavefront cell is one 32-bit word:
+// The M-wavefront ring (depth max(x',i')+1) and both sequences live in shared memory.  Sequences are kept as ONE
+// 32-bit window PER BASE (the 8 bases from that position, first base in the top nibble, built from the 4-bit arena
+// when the pair is fetched): the extension probe of a cell is two plain LDS.32 at (offset - k) and (offset), an XOR
+// and a bfind — no window address arithmetic, no funnel shifts, no bit reversal.
+// Each wavefront cell is one 32-bit word:
 //     [31] null/sign | [30:16] offset h | [15:14] predecessor-type | [13:0] k0 + 8192
 // so that ONE signed max over the three candidates reproduces WFA2's backtrace tie-break
 // (mismatch > deletion > insertion on equal offsets) while carrying k0, the diagonal on which the
@@ -16,12 +19,15 @@
 //
 // Each thread owns 4 consecutive diagonals per iteration (one LDS.128 per source row, one STS.128 out) and
 // runs recurrence, bounds and the first 8-base extend window of the four cells as straight-line code, so
-// the LDS/funnel-shift/XOR/FLO chains of four cells overlap.  Reads of source wavefronts are range-guarded
+// the LDS/XOR/FLO chains of four cells overlap.  Reads of source wavefronts are range-guarded
 // from per-wavefront (lo,hi) metadata, so the ring never needs initialising or clearing.  With a single
 // component, wavefront trimming only ever removes null cells, so it is not performed: the live range is the
-// computed range clamped to the matrix diagonals, and the only per-score reduction is "did a diagonal
-// terminate" (one barrier with OR-reduction for multi-warp groups).
-// Integer-ALU / shared-memory-latency bound; no tensor cores (integer DP).
+// computed range clamped to the matrix diagonals.  That makes every wavefront's range a function of the two source
+// ranges alone, never of cell values: ONE planner thread per group computes the plan of the next existing score
+// (ranges, interior range, ring row offsets) while the group computes the current one, and after the score's single
+// barrier (OR-reduction: "did a diagonal terminate") every thread reads the 12-word plan instead of re-deriving it;
+// scores whose wavefront does not exist cost no barrier.
+// Integer-ALU bound (alu pipe 54-70 % busy, issue ~67 %); no tensor cores (integer DP).
 #pragma once
 #include "sfc_device.cuh"
 
