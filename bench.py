@@ -84,8 +84,9 @@ def make_batch(workload, n_reads, seed):
     return arena, pairs, np.asarray(groups, np.int64)
 
 
-def compact_shard(arena, pairs, idx):
-    """The sequences of pairs[idx] copied into an arena of their own (merged byte intervals, offsets remapped)."""
+def compact_shard(arena, pairs, idx, out=None):
+    """The sequences of pairs[idx] copied into an arena of their own (merged byte intervals, offsets remapped); straight
+    into `out` (the pinned staging buffer) when given."""
     sub = pairs[idx].copy()
     starts = np.concatenate([sub["pattern_off"], sub["text_off"]]).astype(np.int64)
     ends = starts + np.concatenate([sub["pattern_len"], sub["text_len"]]).astype(np.int64)
@@ -99,7 +100,14 @@ def compact_shard(arena, pairs, idx):
     iv_len = iv_end - iv_start
     iv_new = np.concatenate([[0], np.cumsum(iv_len)[:-1]])
     # one slice copy per merged interval (an SV group's sequences are contiguous in the arena: ~ one interval per group)
-    local = np.concatenate([arena[a:b] for a, b in zip(iv_start.tolist(), iv_end.tolist())]) if len(iv_start) else np.zeros(0, np.uint8)
+    total = int(iv_len.sum()) if len(iv_len) else 0
+    if total == 0:
+        local = np.zeros(0, np.uint8)
+    elif out is not None:
+        local = out[:total]
+        np.concatenate([arena[a:b] for a, b in zip(iv_start.tolist(), iv_end.tolist())], out=local)
+    else:
+        local = np.concatenate([arena[a:b] for a, b in zip(iv_start.tolist(), iv_end.tolist())])
     which_p = np.searchsorted(iv_start, sub["pattern_off"].astype(np.int64), side="right") - 1
     which_t = np.searchsorted(iv_start, sub["text_off"].astype(np.int64), side="right") - 1
     sub["pattern_off"] = (sub["pattern_off"].astype(np.int64) - iv_start[which_p] + iv_new[which_p]).astype(np.uint64)
@@ -466,9 +474,8 @@ def run_leg(args, D, ctx, workload, reads, steps, warmup, cpu_budget, local_rank
             tp = time.perf_counter()
             arena, pairs, groups = glob[b]
             mine, _ = sharding.shard_pairs(pen, pairs, groups, world, rank)
-            la, lp = compact_shard(arena, pairs, mine)
             a, p, n = pins[b]
-            a.numpy()[:len(la)] = la
+            la, lp = compact_shard(arena, pairs, mine, out=a.numpy())
             p.numpy()[:lp.nbytes] = lp.view(np.uint8)
             plan_ms += (time.perf_counter() - tp) * 1e3
         r = e2e_step(b)

@@ -279,3 +279,25 @@ def test_matching_debug_view(ctx):
     print_pairwise_alignment(al, pat, file=out)
     rows = out.getvalue().splitlines()
     assert rows[1].replace("-", "").encode() == text and rows[3].replace("-", "").encode() == pat and "|" in rows[2]
+
+
+# (metric, match, mismatch, gap_open1, gap_ext1, gap_open2, gap_ext2): the ABI takes any such set, sawfish uses two of them.
+# Linear: mismatch cheaper / dearer than an indel, with and without a match bonus (the ring depth, which source row is the
+# older one and which scores exist all change); affine-2p: other slopes and a second piece that never / always wins.
+_OTHER_PENALTIES = [
+    (0, 0, 4, 0, 2, 0, 0), (0, 0, 1, 0, 3, 0, 0), (0, -2, 5, 0, 1, 0, 0), (0, -1, 2, 0, 6, 0, 0), (0, 0, 7, 0, 7, 0, 0),
+    (1, 0, 4, 6, 2, 24, 1), (1, -1, 2, 3, 1, 20, 0), (1, 0, 5, 2, 3, 2, 3), (1, -2, 6, 1, 4, 40, 1),
+]
+
+
+@pytest.mark.parametrize("pen_t", _OTHER_PENALTIES, ids=lambda p: "-".join(str(abs(v)) for v in p))
+def test_penalty_sets_other_than_sawfish_presets(ctx, oracle, pen_t):
+    from sawfish_b200 import synth
+    from sawfish_b200.batch import Penalties
+    pen = Penalties(*pen_t)
+    arena, pairs = synth.random_pairs(600, seed=sum(abs(v) * (i + 1) for i, v in enumerate(pen_t)), max_len=300)
+    compare_with_oracle(oracle, ctx, pen, arena, pairs, want_cigar=False, mode=oracle.MODE_LITERAL)
+    compare_with_oracle(oracle, ctx, pen, arena, pairs[:200], want_cigar=True, mode=oracle.MODE_LITERAL)
+    arena, pairs = synth.low_complexity_pairs(40, seed=pen_t[2] * 13 + pen_t[4], len_lo=300, len_hi=1500)
+    compare_with_oracle(oracle, ctx, pen, arena, pairs, want_cigar=False)
+    compare_with_oracle(oracle, ctx, pen, arena, pairs, want_cigar=True)
