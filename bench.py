@@ -84,6 +84,17 @@ def make_batch(workload, n_reads, seed):
     return arena, pairs, np.asarray(groups, np.int64)
 
 
+_COPY_POOL = None
+
+
+def _copy_pool():
+    global _COPY_POOL
+    if _COPY_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _COPY_POOL = ThreadPoolExecutor(max_workers=4)
+    return _COPY_POOL
+
+
 def compact_shard(arena, pairs, idx, out=None):
     """The sequences of pairs[idx] copied into an arena of their own (merged byte intervals, offsets remapped); straight
     into `out` (the pinned staging buffer) when given."""
@@ -104,8 +115,32 @@ def compact_shard(arena, pairs, idx, out=None):
     if total == 0:
         local = np.zeros(0, np.uint8)
     elif out is not None:
+        # straight into the staging buffer, in <= 4 MB pieces on a few host threads (numpy copies release the GIL): the copy
+        # is the whole cost of the compaction (tens of MB per shard)
         local = out[:total]
-        np.concatenate([arena[a:b] for a, b in zip(iv_start.tolist(), iv_end.tolist())], out=local)
+        jobs = []
+        for a, b, d in zip(iv_start.tolist(), iv_end.tolist(), iv_new.tolist()):
+            for o in range(0, b - a, 4 << 20):
+                n = min(4 << 20, b - a - o)
+                jobs.append((a + o, d + o, n))
+
+        def copy(js):
+            for j in js:
+                local[j[1]:j[1] + j[2]] = arena[j[0]:j[0] + j[2]]
+        # four bundles of about equal bytes (a task per interval would cost more in hand-offs than it copies)
+        bundles, cur, acc = [], [], 0
+        for j in jobs:
+            cur.append(j)
+            acc += j[2]
+            if acc >= (total + 3) // 4:
+                bundles.append(cur)
+                cur, acc = [], 0
+        if cur:
+            bundles.append(cur)
+        if len(bundles) > 1:
+            list(_copy_pool().map(copy, bundles))
+        else:
+            copy(jobs)
     else:
         local = np.concatenate([arena[a:b] for a, b in zip(iv_start.tolist(), iv_end.tolist())])
     which_p = np.searchsorted(iv_start, sub["pattern_off"].astype(np.int64), side="right") - 1
