@@ -65,6 +65,9 @@ struct sfc_ctx {
   std::vector<SeqDesc> h_seqs;
   std::vector<uint32_t> h_seqwoff;
   std::vector<uint32_t> h_order;
+  std::vector<uint8_t> h_cls;  // class code of every pair of the batch (classify_pairs)
+  size_t cls_begin[16] = {};   // first position of every class in h_order
+  bool cls_valid = false, cls_k1_ok = false;
   std::vector<int32_t> h_status;
   std::vector<unsigned long long> h_outoff;
   std::vector<uint32_t> h_outlen;
@@ -271,11 +274,56 @@ extern "C" int sfc_set_workspace_limit(sfc_ctx* c, size_t bytes) {
 }
 
 // ============================================================================ upload
+// Work order of a batch: counting sort by class (K1 size classes 0..11, then small / large K2 pairs), two linear passes
+// over the pairs — at 10^5-10^6 pairs per batch this is on the end-to-end path, so sfc_batch_upload runs it while the
+// arena copy is in flight (for the K1-eligible case; sfc_batch_run redoes it when the penalties rule K1 out).
+void classify_pairs(sfc_ctx* c, bool k1_ok) {
+  constexpr int kSmall = kNumK1Classes, kLarge = kNumK1Classes + 1, kCodes = kNumK1Classes + 2;
+  const size_t n = c->n_pairs;
+  uint8_t cls_of[40];  // K1 class of a ring-row width W, by ceil(W / 128) (every class capacity is a multiple of 128)
+  for (int q = 0; q < 40; ++q) {
+    cls_of[q] = 0xFF;
+    for (int j = 0; j < kNumK1Classes; ++j) if (q * 128 <= kK1Classes[j].wcap) { cls_of[q] = (uint8_t)j; break; }
+  }
+  c->h_cls.resize(n);
+  size_t count[kCodes] = {};
+  for (size_t i = 0; i < n; ++i) {
+    const DevPair& d = c->h_pairs[i];
+    const long long W = (long long)d.plen + d.tlen + 12;  // ring row: diagonals -plen-1..tlen+1 plus vector-group slack
+    int code = W <= 4096 + 7 ? kSmall : kLarge;
+    if (k1_ok && W <= 39 * 128 && d.plen <= K1_MAX_LEN && d.tlen <= K1_MAX_LEN && d.pbf <= K1_MAX_FREE && d.tbf <= K1_MAX_FREE) {
+      const uint8_t cl = cls_of[(W + 127) >> 7];
+      if (cl != 0xFF) code = cl;
+    }
+    c->h_cls[i] = (uint8_t)code;
+    ++count[code];
+  }
+  c->cls_begin[0] = 0;
+  for (int q = 0; q < kCodes; ++q) c->cls_begin[q + 1] = c->cls_begin[q] + count[q];
+  c->h_order.resize(n);
+  {
+    size_t pos[kCodes];
+    for (int q = 0; q < kCodes; ++q) pos[q] = c->cls_begin[q];
+    for (size_t i = 0; i < n; ++i) c->h_order[pos[c->h_cls[i]]++] = (uint32_t)i;  // stable: no sort inside a K1 class (the groups pull pairs dynamically)
+  }
+  auto sort_heavy_first = [&](size_t b, size_t e) {
+    std::stable_sort(c->h_order.begin() + b, c->h_order.begin() + e, [&](uint32_t x, uint32_t y) {
+      const long long wx = (long long)c->h_pairs[x].plen + c->h_pairs[x].tlen, wy = (long long)c->h_pairs[y].plen + c->h_pairs[y].tlen;
+      return (wx >> 6) > (wy >> 6);
+    });
+  };
+  sort_heavy_first(c->cls_begin[kSmall], c->cls_begin[kLarge]);
+  sort_heavy_first(c->cls_begin[kLarge], n);
+  c->cls_valid = true;
+  c->cls_k1_ok = k1_ok;
+}
+
 extern "C" int sfc_batch_upload(sfc_ctx* c, const uint8_t* arena, size_t arena_len, const sfc_pair* pairs, size_t n) {
   if (!c) return SFC_ERR_INVALID;
   if (!arena || !pairs || n == 0 || n > 0x7FFFFFF0u) return fail(c, SFC_ERR_INVALID, "null/empty batch");
   CU(cudaSetDevice(c->device));
   c->uploaded = c->ran = false;
+  c->cls_valid = false;
   c->n_pairs = n;
   c->h_pairs.resize(n);
   c->h_seqs.resize(2 * n);
@@ -333,6 +381,7 @@ extern "C" int sfc_batch_upload(sfc_ctx* c, const uint8_t* arena, size_t arena_l
   c->stats = sfc_batch_stats{};
   c->stats.h2d_bytes = arena_len + 2 * n * sizeof(SeqDesc) + (2 * n + 1) * 4 + n * sizeof(DevPair);
   c->stats.launches = 1;
+  classify_pairs(c, true);  // hidden behind the arena copy
   // the caller's arena has been read completely (include/sawfish_cuda.h: buffer lifetime); the pack kernel keeps running
   CU(cudaEventSynchronize(c->ev[7]));
   c->uploaded = true;
@@ -359,41 +408,13 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
 
   // ---- classify pairs ----
   const int lookL = std::max(a.x, a.e1);
-  std::vector<uint32_t> k1_lists[kNumK1Classes];
-  std::vector<uint32_t> k2_small, k2_large;
-  for (size_t i = 0; i < n; ++i) {
-    const DevPair& d = c->h_pairs[i];
-    const long long W = (long long)d.plen + d.tlen + 12;  // ring row: diagonals -plen-1..tlen+1 plus vector-group slack
-    bool k1 = (a.metric == 0) && !want_cigar && d.plen <= K1_MAX_LEN && d.tlen <= K1_MAX_LEN && d.pbf <= K1_MAX_FREE &&
-              d.tbf <= K1_MAX_FREE && lookL <= 32;
-    if (k1) {
-      int cls = -1;
-      for (int j = 0; j < kNumK1Classes; ++j) if (W <= kK1Classes[j].wcap) { cls = j; break; }
-      if (cls >= 0) { k1_lists[cls].push_back((uint32_t)i); continue; }
-    }
-    if (W <= 4096 + 7) k2_small.push_back((uint32_t)i); else k2_large.push_back((uint32_t)i);
-  }
-  auto sort_heavy_first = [&](std::vector<uint32_t>& v) {
-    std::stable_sort(v.begin(), v.end(), [&](uint32_t x, uint32_t y) {
-      const long long wx = (long long)c->h_pairs[x].plen + c->h_pairs[x].tlen, wy = (long long)c->h_pairs[y].plen + c->h_pairs[y].tlen;
-      return (wx >> 6) > (wy >> 6);
-    });
-  };
-  c->h_order.clear();
+  const bool k1_ok = (a.metric == 0) && !want_cigar && lookL <= 32;
+  // (sfc_batch_upload has classified the batch for the K1-eligible case while the arena copy was in flight)
+  if (!c->cls_valid || c->cls_k1_ok != k1_ok) classify_pairs(c, k1_ok);
+  constexpr int kSmall = kNumK1Classes, kLarge = kNumK1Classes + 1;
   size_t k1_begin[kNumK1Classes + 1];
-  for (int j = 0; j < kNumK1Classes; ++j) {
-    // no sort inside a K1 class: the classes are narrow in size and the groups pull pairs dynamically, while an
-    // O(n log n) host sort of ~10^5-10^6 pairs per batch shows up in the end-to-end time
-    k1_begin[j] = c->h_order.size();
-    c->h_order.insert(c->h_order.end(), k1_lists[j].begin(), k1_lists[j].end());
-  }
-  k1_begin[kNumK1Classes] = c->h_order.size();
-  sort_heavy_first(k2_small);
-  sort_heavy_first(k2_large);
-  const size_t k2s_begin = c->h_order.size();
-  c->h_order.insert(c->h_order.end(), k2_small.begin(), k2_small.end());
-  const size_t k2l_begin = c->h_order.size();
-  c->h_order.insert(c->h_order.end(), k2_large.begin(), k2_large.end());
+  for (int j = 0; j <= kNumK1Classes; ++j) k1_begin[j] = c->cls_begin[j];
+  const size_t k2s_begin = c->cls_begin[kSmall], k2l_begin = c->cls_begin[kLarge];
   c->stats.n_score_kernel = (uint32_t)k2s_begin;
   c->stats.n_align_kernel = (uint32_t)(n - k2s_begin);
 
@@ -790,7 +811,8 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     if ((rc = reset_pool())) return rc;
     CU(cudaMemsetAsync(misc + 8, 0, 32, c->stream));
     {
-      // rewrite the K2 part of the order array job by job
+      // rewrite the K2 part of the order array job by job (a later run on the same upload classifies afresh)
+      c->cls_valid = false;
       size_t pos = k2s_begin;
       for (auto& j : jobs) { std::copy(j.list.begin(), j.list.end(), c->h_order.begin() + pos); pos += j.list.size(); }
       CU(cudaMemcpyAsync((uint32_t*)c->d_order.p + k2s_begin, c->h_order.data() + k2s_begin, (n - k2s_begin) * 4, cudaMemcpyHostToDevice, c->stream));
