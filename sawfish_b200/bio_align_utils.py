@@ -3,8 +3,8 @@
 Same names and argument order as the Rust: `align(text, pattern)` returns the score, `get_last_alignment()` the
 SimpleAlignment built by `bio_alignment_to_simple_alignment` (:16-64), `rescore_alignment` (:71-94), the four
 aligner constructors (:97-165) and `OverlapPairwiseAligner` (:207-270).  x = pattern, y = text as in rust-bio.
-The reference seeds a band from k-mer matches (k, w); the CUDA path fills the whole matrix, so k and w are accepted
-and ignored.  `align_batch` is the batched form the GPU wants (one launch for many (text, pattern) pairs).
+The reference seeds a band from k-mer matches (k, w); the CUDA path fills the whole matrix: w is accepted and ignored,
+k only feeds `find_kmer_matches`, which tells when the two are the same thing (`band_free`).  `align_batch` is the batched form the GPU wants (one launch for many (text, pattern) pairs).
 """
 from __future__ import annotations
 
@@ -72,7 +72,26 @@ def rescore_alignment(cigar: Sequence[Cigar], weights: AlignmentWeights) -> int:
     return score
 
 
+def find_kmer_matches(seq1: bytes, seq2: bytes, k: int) -> List[Tuple[int, int]]:
+    """rust-bio `alignment::sparse::find_kmer_matches` as the reference calls it (src/bio_align_utils.rs:169): every
+    (i, j) with seq1[i:i+k] == seq2[j:j+k], sorted.  Used here only to tell whether the reference's band degenerates to
+    the full matrix (no match at all) — the band construction itself is not restated."""
+    if k <= 0 or len(seq1) < k or len(seq2) < k:
+        return []
+    index = {}
+    for i in range(len(seq1) - k + 1):
+        index.setdefault(seq1[i:i + k], []).append(i)
+    out = []
+    for j in range(len(seq2) - k + 1):
+        for i in index.get(seq2[j:j + k], ()):
+            out.append((i, j))
+    out.sort()
+    return out
+
+
 class PairwiseAligner:
+    band_free = False  # True after an align() whose pair shares no k-mer: rust-bio fills the whole matrix there as well
+
     def __init__(self, ctx, scoring: BioScoring, k: int = 20, w: int = 10):
         self.ctx, self.scoring, self.k, self.w = ctx, scoring, k, w
         self.alignment: Optional[BioAlignment] = None
@@ -144,11 +163,15 @@ class PairwiseAligner:
         return [int(v) for v in scores]
 
     def align(self, text: bytes, pattern: bytes) -> int:  # :168-172
-        self.alignment = self.align_batch([(text, pattern)])[0]
-        return self.alignment.score
+        return self.align_with_matches(text, pattern, find_kmer_matches(pattern, text, self.k))
 
     def align_with_matches(self, text: bytes, pattern: bytes, matches=None) -> int:  # :175-186 (matches only shape the band)
-        return self.align(text, pattern)
+        """`matches` do not change what the GPU computes (full matrix); they decide what can be CLAIMED about it:
+        with no k-mer match rust-bio's band is the full matrix too (`band_free` True: identical by construction),
+        otherwise the reference result is the optimum inside a band this repo does not restate."""
+        self.band_free = matches is not None and len(matches) == 0
+        self.alignment = self.align_batch([(text, pattern)])[0]
+        return self.alignment.score
 
     def get_last_alignment(self) -> Optional[SimpleAlignment]:  # :188-191
         return None if self.alignment is None else bio_alignment_to_simple_alignment(self.alignment)

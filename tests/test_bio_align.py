@@ -121,6 +121,23 @@ def _to_gpu_scoring(sc):
                       sc.yclip_suffix)
 
 
+def test_find_kmer_matches_is_every_shared_kmer_sorted():
+    """`find_kmer_matches` (what `align` hands to rust-bio, src/bio_align_utils.rs:169) against a brute-force scan; with no
+    shared k-mer the reference's band is the full matrix, which is where this repo's full-matrix result is identical by
+    construction (`band_free`)."""
+    import numpy as np
+    from sawfish_b200.bio_align_utils import find_kmer_matches
+    rng = np.random.default_rng(5)
+    for k in (3, 5, 20):
+        x = bytes(rng.choice(list(b"ACGT"), 300).tolist())
+        y = x[40:180] + bytes(rng.choice(list(b"ACGT"), 60).tolist()) + x[200:260]
+        want = sorted((i, j) for i in range(len(x) - k + 1) for j in range(len(y) - k + 1) if x[i:i + k] == y[j:j + k])
+        assert find_kmer_matches(x, y, k) == want
+        assert len(want) > 0
+    assert find_kmer_matches(b"ACGT", b"ACGTACGT", 20) == []       # shorter than k
+    assert find_kmer_matches(TEXT, b"ACGTAC", 20) == []             # every known answer of the reference is band free
+
+
 @pytest.mark.gpu
 def test_host_mirror_replays_reference_tests():
     """The reference's own unit tests (src/bio_align_utils.rs:291-403) through the CUDA path and the host mirror."""
@@ -136,6 +153,7 @@ def test_host_mirror_replays_reference_tests():
     for flavour, pattern, score, aln in KNOWN:
         a = makers[flavour]()
         assert a.align(TEXT, pattern) == score
+        assert a.band_free  # no shared 20-mer: rust-bio fills the whole matrix here too, so these answers pin K4 exactly
         if aln is not None:
             got = a.get_last_alignment()
             assert (got.ref_offset, cigar_to_string(got.cigar)) == aln
