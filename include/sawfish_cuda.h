@@ -159,7 +159,9 @@ int sfc_estimate_pair_work(const sfc_penalties*, const sfc_pair* pairs, size_t n
 int sfc_shard_plan(const uint64_t* group_work, size_t n_groups, int n_shards, uint32_t* shard_of_group);
 
 /* ---- one process, several GPUs: the deployment shape of the reference (one rayon pool, no MPI) ----
- * sfc_multi owns one sfc_ctx + one submitter thread per device.  A batch is split by SV group with sfc_shard_plan
+ * sfc_multi owns submitter threads and contexts per device: two of each for score-only gap-linear batches (the
+ * score_sv shape: one sub-shard's host staging overlaps the other's kernels on the same GPU; SFC_MULTI_SPLIT=1..4
+ * changes the count), one otherwise.  A batch is split by SV group with sfc_shard_plan
  * (group_of_pair == NULL: every pair is its own group), each shard gets a compacted copy of just its sequences,
  * shards run concurrently on their GPUs, and results are gathered on the host in the caller's pair order.
  * No collective, no peer access: batches are independent (north_star). Replaces the fan-out / mpsc gather of
@@ -173,7 +175,8 @@ int sfc_multi_align_batch(sfc_multi*, const sfc_penalties*, const uint8_t* seq_a
                           const sfc_pair* pairs, size_t n_pairs, const uint32_t* group_of_pair,
                           int want_cigar, int32_t* scores, int32_t* status,
                           uint32_t* ops_rle, size_t ops_cap, uint64_t* ops_off);
-/* kernel milliseconds of the last batch on each device (max = the batch's device time). out: [n_devices] */
+/* kernel milliseconds of the last batch on each device, summed over the device's contexts (their kernels share the
+ * GPU, so this bounds the time the device was busy from above). out: [n_devices] */
 int sfc_multi_last_kernel_ms(const sfc_multi*, double* out);
 
 /* ---- measurement helper: integer-ALU roofline denominator (IADD3/LOP3 issue rate) ---- */

@@ -1205,8 +1205,11 @@ extern "C" int sfc_shard_plan(const uint64_t* group_work, size_t n_groups, int n
 
 // ============================================================================ one process, several GPUs
 struct sfc_multi {
+  // `split` contexts (and submitter threads) per device: a score-only batch is cut into n_dev x split shards so that one
+  // sub-shard's host staging (compaction, upload) overlaps the other's kernels on the same GPU.  ctx[d * split + j].
+  int n_dev = 0, split = 1;
   std::vector<sfc_ctx*> ctx;
-  std::vector<double> kernel_ms;
+  std::vector<double> kernel_ms;  // per context
   std::string err;
   // per-shard pinned staging (grow-only): compacted arena, pair table, results
   struct Stage {
@@ -1237,14 +1240,19 @@ extern "C" int sfc_multi_create(const int* devs, int n, sfc_multi** out) {
   *out = nullptr;
   sfc_multi* m = new (std::nothrow) sfc_multi();
   if (!m) return SFC_ERR_OOM;
+  m->n_dev = n;
+  m->split = 2;
+  if (const char* e = getenv("SFC_MULTI_SPLIT")) m->split = std::max(1, std::min(4, atoi(e)));
   for (int i = 0; i < n; ++i) {
-    sfc_ctx* c = nullptr;
-    const int rc = sfc_create(devs[i], &c);
-    if (rc) { sfc_multi_destroy(m); return rc; }
-    m->ctx.push_back(c);
+    for (int j = 0; j < m->split; ++j) {
+      sfc_ctx* c = nullptr;
+      const int rc = sfc_create(devs[i], &c);
+      if (rc) { sfc_multi_destroy(m); return rc; }
+      m->ctx.push_back(c);
+    }
   }
-  m->kernel_ms.assign((size_t)n, 0.0);
-  m->stage.resize((size_t)n);
+  m->kernel_ms.assign(m->ctx.size(), 0.0);
+  m->stage.resize(m->ctx.size());
   *out = m;
   return SFC_OK;
 }
@@ -1261,12 +1269,16 @@ extern "C" void sfc_multi_destroy(sfc_multi* m) {
   delete m;
 }
 
-extern "C" int sfc_multi_device_count(const sfc_multi* m) { return m ? (int)m->ctx.size() : 0; }
+extern "C" int sfc_multi_device_count(const sfc_multi* m) { return m ? m->n_dev : 0; }
 extern "C" const char* sfc_multi_last_error(const sfc_multi* m) { return m ? m->err.c_str() : "null"; }
 
 extern "C" int sfc_multi_last_kernel_ms(const sfc_multi* m, double* out) {
   if (!m || !out) return SFC_ERR_INVALID;
-  for (size_t i = 0; i < m->kernel_ms.size(); ++i) out[i] = m->kernel_ms[i];
+  // per device: the sum over its contexts (their kernels share the GPU, so this is an upper bound of the time it was busy)
+  for (int d = 0; d < m->n_dev; ++d) {
+    out[d] = 0.0;
+    for (int j = 0; j < m->split; ++j) out[d] += m->kernel_ms[(size_t)d * m->split + j];
+  }
   return SFC_OK;
 }
 
@@ -1275,7 +1287,12 @@ extern "C" int sfc_multi_align_batch(sfc_multi* m, const sfc_penalties* pen, con
                                      int32_t* scores, int32_t* status, uint32_t* ops_rle, size_t ops_cap, uint64_t* ops_off) {
   if (!m || !pen || !arena || !pairs || !scores || !status || n == 0) return SFC_ERR_INVALID;
   if (want_cigar && !ops_off) return SFC_ERR_INVALID;
-  const int nd = (int)m->ctx.size();
+  // shards: `split` per device for a score-only gap-linear batch (K1: no workspace, kernels of two contexts share a GPU
+  // well), one per device otherwise (two K2 runs would each size their workspace for the whole device)
+  std::fill(m->kernel_ms.begin(), m->kernel_ms.end(), 0.0);
+  const int split = (pen->metric == 0 && !want_cigar) ? m->split : 1;
+  const int nd = m->n_dev * split;
+  auto ctx_of = [&](int d) -> size_t { return (size_t)(d / split) * m->split + (size_t)(d % split); };
   // ---- plan: LPT over groups by estimated work.  Without caller groups, runs of consecutive pairs form the groups
   // (consecutive pairs share reads / loci in the callers), which keeps the plan O(n) instead of a sort over every pair.
   // (the per-pair estimate and the bounds check are split over a few host threads: at 10^5-10^6 pairs per batch the
@@ -1319,15 +1336,18 @@ extern "C" int sfc_multi_align_batch(sfc_multi* m, const sfc_penalties* pen, con
     int rc = 0;
   };
   std::vector<Shard> sh((size_t)nd);
-  for (int d = 0; d < nd; ++d) sh[(size_t)d].idx.reserve(n / (size_t)nd + n / 8 + 16);
-  for (size_t i = 0; i < n; ++i) sh[shard_of_group[group_of(i)]].idx.push_back((uint32_t)i);
   // ---- one submitter thread per GPU: sizing (pass 1), compaction (pass 2), upload, kernels, download ----
   std::vector<std::thread> th;
   for (int d = 0; d < nd; ++d) {
     th.emplace_back([&, d]() {
       Shard& s = sh[(size_t)d];
-      sfc_multi::Stage& st = m->stage[(size_t)d];
-      m->kernel_ms[(size_t)d] = 0.0;
+      const size_t ci = ctx_of(d);
+      sfc_multi::Stage& st = m->stage[ci];
+      m->kernel_ms[ci] = 0.0;
+      // this shard's pair list: every submitter scans the plan itself (a serial fill of all lists would sit in front of
+      // every GPU's work)
+      s.idx.reserve(n / (size_t)nd + n / 8 + 16);
+      for (size_t i = 0; i < n; ++i) if (shard_of_group[group_of(i)] == (uint32_t)d) s.idx.push_back((uint32_t)i);
       if (s.idx.empty()) return;
       {
         uint64_t lt_off = ~0ull;
@@ -1338,7 +1358,7 @@ extern "C" int sfc_multi_align_batch(sfc_multi* m, const sfc_penalties* pen, con
           if (!(q.text_off == lt_off && q.text_len == lt_len)) { bytes += q.text_len; lt_off = q.text_off; lt_len = q.text_len; }
           bytes += q.pattern_len;
         }
-        cudaSetDevice(m->ctx[(size_t)d]->device);
+        cudaSetDevice(m->ctx[ci]->device);
         if (pinned_reserve(st.arena, st.arena_cap, bytes) || pinned_reserve(st.pairs, st.pairs_cap, s.idx.size()) ||
             pinned_reserve(st.scores, st.scores_cap, s.idx.size()) || pinned_reserve(st.status, st.status_cap, s.idx.size())) {
           s.rc = SFC_ERR_OOM;
@@ -1346,22 +1366,40 @@ extern "C" int sfc_multi_align_batch(sfc_multi* m, const sfc_penalties* pen, con
         }
         s.arena_bytes = bytes;
       }
+      // pass 2: new offsets (serial, a few ns per pair), then the copies themselves on a few threads: ~0.1 us per pair in
+      // two small memcpys is 50 ms for a 5 x 10^5-pair shard on one thread, more than the shard's share of the kernels
       uint64_t last_t_off = ~0ull, last_t_new = 0, pos = 0;
       uint32_t last_t_len = 0;
+      std::vector<uint8_t> own_text(s.idx.size());
       for (size_t j = 0; j < s.idx.size(); ++j) {
         sfc_pair q = pairs[s.idx[j]];
-        if (q.text_off == last_t_off && q.text_len == last_t_len) q.text_off = last_t_new;
+        if (q.text_off == last_t_off && q.text_len == last_t_len) { q.text_off = last_t_new; own_text[j] = 0; }
         else {
           last_t_off = q.text_off; last_t_len = q.text_len; last_t_new = pos;
-          memcpy(st.arena + pos, arena + q.text_off, q.text_len);
           q.text_off = pos; pos += q.text_len;
+          own_text[j] = 1;
         }
-        memcpy(st.arena + pos, arena + q.pattern_off, q.pattern_len);
         q.pattern_off = pos; pos += q.pattern_len;
         st.pairs[j] = q;
       }
+      {
+        const size_t np_ = s.idx.size();
+        const size_t T = std::max<size_t>(1, std::min<size_t>(4, np_ / 16384));
+        auto copy_range = [&](size_t b, size_t e) {
+          for (size_t j = b; j < e; ++j) {
+            const sfc_pair& o = pairs[s.idx[j]];
+            const sfc_pair& q = st.pairs[j];
+            if (own_text[j]) memcpy(st.arena + q.text_off, arena + o.text_off, o.text_len);
+            memcpy(st.arena + q.pattern_off, arena + o.pattern_off, o.pattern_len);
+          }
+        };
+        std::vector<std::thread> ct;
+        for (size_t t = 1; t < T; ++t) ct.emplace_back(copy_range, np_ * t / T, np_ * (t + 1) / T);
+        copy_range(0, np_ / T);
+        for (auto& t : ct) t.join();
+      }
       if (want_cigar) { s.ops_off.resize(s.idx.size() + 1); s.ops.resize(std::max<size_t>(s.idx.size() * 64, 1 << 16)); }
-      sfc_ctx* c = m->ctx[(size_t)d];
+      sfc_ctx* c = m->ctx[ci];
       s.rc = sfc_batch_upload(c, st.arena, s.arena_bytes, st.pairs, s.idx.size());
       if (!s.rc) s.rc = sfc_batch_run(c, pen, want_cigar);
       if (!s.rc) {
@@ -1376,13 +1414,13 @@ extern "C" int sfc_multi_align_batch(sfc_multi* m, const sfc_penalties* pen, con
         for (size_t j = 0; j < s.idx.size(); ++j) { scores[s.idx[j]] = st.scores[j]; status[s.idx[j]] = st.status[j]; }
       }
       sfc_batch_stats bs;
-      if (!sfc_batch_get_stats(c, &bs)) m->kernel_ms[(size_t)d] = bs.kernel_ms;
+      if (!sfc_batch_get_stats(c, &bs)) m->kernel_ms[ci] = bs.kernel_ms;
     });
   }
   for (auto& t : th) t.join();
   for (int d = 0; d < nd; ++d) {
     if (sh[(size_t)d].rc == SFC_ERR_OOM && sh[(size_t)d].arena_bytes == 0) { m->err = "pinned staging allocation failed"; return SFC_ERR_OOM; }
-    if (sh[(size_t)d].rc) { m->err = std::string("device ") + std::to_string(d) + ": " + sfc_last_error(m->ctx[(size_t)d]); return sh[(size_t)d].rc; }
+    if (sh[(size_t)d].rc) { m->err = std::string("device ") + std::to_string(d / split) + ": " + sfc_last_error(m->ctx[ctx_of(d)]); return sh[(size_t)d].rc; }
   }
   if (want_cigar) {
     std::vector<uint32_t> where(n);
