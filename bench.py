@@ -439,16 +439,29 @@ def run_leg(args, D, ctx, workload, reads, steps, warmup, cpu_budget, local_rank
         n_tot = len(glob[b][1])
         g_scores = np.zeros(n_tot, np.int32)
         seen = np.zeros(n_tot, bool)
-        g_ops = [None] * n_tot if want_cigar else None
+        g_len = np.zeros(n_tot, np.int64)
         for idx, sc, op, off in got:
             assert not seen[idx].any(), "a pair was assigned to two ranks"
             g_scores[idx] = sc
             seen[idx] = True
             if want_cigar:
-                for j, gi in enumerate(idx):
-                    g_ops[gi] = op[int(off[j]):int(off[j + 1])]
+                g_len[idx] = np.diff(np.asarray(off, np.int64))
         assert seen.all(), "a pair was assigned to no rank"
-        return g_scores, g_ops, None
+        if not want_cigar:
+            return g_scores, None, None
+        # run-length ops of every rank scattered into ONE array in global pair order (no per-pair Python loop: this is
+        # inside the timed end-to-end step)
+        g_off = np.zeros(n_tot + 1, np.int64)
+        np.cumsum(g_len, out=g_off[1:])
+        g_ops = np.zeros(int(g_off[-1]), np.uint32)
+        for idx, sc, op, off in got:
+            off = np.asarray(off, np.int64)
+            lens = np.diff(off)
+            tot = int(off[-1] - off[0])
+            if tot:
+                dest = np.repeat(g_off[:-1][idx] - off[:-1], lens) + np.arange(int(off[0]), int(off[0]) + tot)
+                g_ops[dest] = np.asarray(op)[int(off[0]):int(off[0]) + tot]
+        return g_scores, g_ops, g_off
 
     # ---- warm-up (also allocates device workspace) ----
     # At least W (>= 3) steps AND at least ~2.5 s: the first GPU process on a fresh box runs its first few hundred
@@ -575,7 +588,7 @@ def run_leg(args, D, ctx, workload, reads, steps, warmup, cpu_budget, local_rank
     ops_mism = 0
     if want_cigar:
         for i in range(m):
-            got = g_ops[i] if world > 1 else g_ops[int(g_off[i]):int(g_off[i + 1])]
+            got = g_ops[int(g_off[i]):int(g_off[i + 1])]
             want = cb["ops_rle"][i]
             if len(got) != len(want) or not (np.asarray(got) == want).all():
                 ops_mism += 1
