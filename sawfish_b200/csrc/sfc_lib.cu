@@ -1,3 +1,4 @@
+#include <chrono>
 // sfc_lib.cu — host side of libsawfish_cuda.so: the C ABI declared in include/sawfish_cuda.h.
 //
 // One sfc_ctx owns one CUDA stream and every device buffer of one GPU.  A batch goes
@@ -60,6 +61,12 @@ struct sfc_ctx {
   // batch state
   size_t n_pairs = 0;
   bool uploaded = false, ran = false;
+  // Free device memory as of the last cudaMemGetInfo, kept up to date with this context's own allocations.  The query itself
+  // is not repeated per batch: with ~150 GB allocated it takes 1-3 ms and now and then 20-90 ms (measured on B200: one
+  // config2 step in ten took 100-170 ms instead of 76 with the kernels waiting for the host), so it is redone only after an
+  // allocation failed (another context / process took the memory).
+  size_t free_cache = 0;
+  bool free_valid = false, free_fresh = false;
   int want_cigar = 0;
   std::vector<DevPair> h_pairs;
   std::vector<SeqDesc> h_seqs;
@@ -110,6 +117,7 @@ int ensure(sfc_ctx* c, DevBuf& b, size_t bytes) {
   if (b.p) {
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaFree(b.p));
+    c->free_cache += b.cap;
     b.p = nullptr;
     b.cap = 0;
   }
@@ -122,10 +130,25 @@ int ensure(sfc_ctx* c, DevBuf& b, size_t bytes) {
   }
   if (e != cudaSuccess) {
     b.p = nullptr;
+    c->free_valid = false;  // somebody else holds memory we counted on: ask the driver again next time
     return fail(c, SFC_ERR_OOM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
   }
   b.cap = want;
+  c->free_cache = c->free_cache > want ? c->free_cache - want : 0;
   return 0;
+}
+
+// free device memory (see sfc_ctx::free_cache)
+size_t device_free_bytes(sfc_ctx* c) {
+  c->free_fresh = false;
+  if (!c->free_valid) {
+    size_t f = 0, t = 0;
+    if (cudaMemGetInfo(&f, &t) != cudaSuccess) { (void)cudaGetLastError(); f = 0; }
+    c->free_cache = f;
+    c->free_valid = true;
+    c->free_fresh = true;
+  }
+  return c->free_cache;
 }
 
 void release(DevBuf& b) {
@@ -237,8 +260,16 @@ extern "C" int sfc_create(int device_ordinal, sfc_ctx** out) {
   for (auto& e : c->ev) {
     if (cudaEventCreate(&e) != cudaSuccess) { sfc_destroy(c); return SFC_ERR_CUDA; }
   }
-  for (auto& st : c->job_stream) {
-    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { sfc_destroy(c); return SFC_ERR_CUDA; }
+  {
+    // job streams 0-3 have the highest priority, 4-5 the lowest: the K2 cluster jobs go on the former, the persistent
+    // single-CTA job on the latter.  Without it the block scheduler now and then starts the single-CTA job first, its
+    // CTAs take every slot for the whole step, and the clusters (which need 2-8 free slots in one GPC at once) only start
+    // when it ends: sporadic steps of 150 ms instead of 76 (same per-CTA cycle counts, serialised jobs).
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { least = greatest = 0; }
+    for (int q = 0; q < 6; ++q) {
+      if (cudaStreamCreateWithPriority(&c->job_stream[q], cudaStreamNonBlocking, q < 4 ? greatest : least) != cudaSuccess) { sfc_destroy(c); return SFC_ERR_CUDA; }
+    }
   }
   for (auto& e : c->job_ev) {
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { sfc_destroy(c); return SFC_ERR_CUDA; }
@@ -391,11 +422,23 @@ extern "C" int sfc_batch_upload(sfc_ctx* c, const uint8_t* arena, size_t arena_l
 // ============================================================================ run
 // d_misc layout (uint32 words): [2..3] cells (u64), [4..5] pool_used (u64), [16..27] K1 class work counters,
 // [8] K2 work counter, [32] bad-symbol flag.
+static int batch_run_impl(sfc_ctx* c, const sfc_penalties* pen, int want_cigar);
+
 extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_cigar) {
+  if (!c) return SFC_ERR_INVALID;
+  const int rc = batch_run_impl(c, pen, want_cigar);
+  // out of memory while planning with a remembered free-memory figure (sfc_ctx::free_cache): the failed allocation has
+  // invalidated it, so plan once more against what the driver reports now
+  if (rc == SFC_ERR_OOM && !c->free_fresh && c->uploaded) return batch_run_impl(c, pen, want_cigar);
+  return rc;
+}
+
+static int batch_run_impl(sfc_ctx* c, const sfc_penalties* pen, int want_cigar) {
   if (!c) return SFC_ERR_INVALID;
   if (!c->uploaded) return fail(c, SFC_ERR_INVALID, "sfc_batch_run before sfc_batch_upload");
   AdjPen a;
   if (adjust_penalties(pen, &a)) return fail(c, SFC_ERR_INVALID, "invalid penalties");
+  const auto t_run_entry = std::chrono::steady_clock::now();
   CU(cudaSetDevice(c->device));
   const size_t n = c->n_pairs;
   int rc;
@@ -485,8 +528,17 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
   // ---- K2 launches: jobs by (size class, cluster size), heaviest first, with workspace escalation ----
   c->pool_used = 0;
   if (k2s_begin < n) {
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
+    size_t free_b = 0;
+    std::string laps;
+    auto lap = [&](const char* what) {
+      if (!getenv("SFC_K2_PROF")) return;
+      char buf[64];
+      snprintf(buf, sizeof buf, " %s %.2f", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run_entry).count());
+      laps += buf;
+    };
+    lap("k2-begin");
+    free_b = device_free_bytes(c);
+    lap("meminfo");
     size_t avail = (size_t)((double)(free_b + c->d_ws.cap + c->d_pool.cap + c->d_pages.cap) * 0.85);
     if (c->ws_limit && avail > c->ws_limit) avail = c->ws_limit;
     size_t pool_cap = want_cigar ? std::max<size_t>((n - k2s_begin) * 64, (size_t)1 << 20) : 16;
@@ -751,6 +803,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
     };
     // ---- first pass: all jobs back to back on the stream (heaviest clusters first) ----
     // Each job owns a slice of the workspace, of the order array and its own work counter.
+    lap("jobs-built");
     std::vector<Plan> plans(jobs.size());
     {
       // split the budget in proportion to demand, then allocate once
@@ -808,7 +861,9 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       CU(cudaMemcpyAsync(c->d_pairpages.p, c->h_pairpages.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
       return 0;
     };
+    lap("planned+pool");
     if ((rc = reset_pool())) return rc;
+    lap("pool-reset");
     CU(cudaMemsetAsync(misc + 8, 0, 32, c->stream));
     {
       // rewrite the K2 part of the order array job by job (a later run on the same upload classifies afresh)
@@ -821,15 +876,50 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
       // jobs run concurrently on their own streams (fork from / join to the ctx stream with events): cluster jobs
       // take whole SMs first, single-CTA jobs fill whatever is free and take over as clusters drain
       CU(cudaEventRecord(c->job_ev[6], c->stream));
+      int n_hi = 0, n_lo = 0;
+      const bool prof_jobs = getenv("SFC_K2_PROF") != nullptr;
+      std::vector<cudaEvent_t> prof_ev;
+      std::vector<std::string> prof_desc;
+      if (prof_jobs) {  // the fork point on the GPU's time line, and how long the host took to get here
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        CU(cudaEventRecord(e, c->stream));
+        prof_ev.push_back(e);
+        char buf[96];
+        snprintf(buf, sizeof buf, "fork; host %.2f ms after run() entry;", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run_entry).count());
+        prof_desc.push_back(std::string(buf) + laps);
+      }
       for (size_t j = 0; j < jobs.size(); ++j) {
-        cudaStream_t st = c->job_stream[j % 6];
+        const int sq = jobs[j].C > 1 ? (n_hi++ % 4) : 4 + (n_lo++ % 2);  // clusters first (stream priority, see sfc_create)
+        cudaStream_t st = c->job_stream[sq];
         CU(cudaStreamWaitEvent(st, c->job_ev[6], 0));
         if ((rc = launch_job((const uint32_t*)c->d_order.p + pos, jobs[j].list.size(), jobs[j].threads, jobs[j].C, plans[j],
                              (unsigned char*)c->d_ws.p + ws_off, misc + 8 + j, st))) return rc;
-        CU(cudaEventRecord(c->job_ev[j % 6], st));
-        CU(cudaStreamWaitEvent(c->stream, c->job_ev[j % 6], 0));
+        CU(cudaEventRecord(c->job_ev[sq], st));
+        CU(cudaStreamWaitEvent(c->stream, c->job_ev[sq], 0));
+        if (prof_jobs) {  // when did each job END, counted from the start of the run's kernel section
+          cudaEvent_t e;
+          CU(cudaEventCreate(&e));
+          CU(cudaEventRecord(e, st));
+          prof_ev.push_back(e);
+          prof_desc.push_back(std::string("C=") + std::to_string(jobs[j].C) + " thr=" + std::to_string(jobs[j].threads) + " pairs=" + std::to_string(jobs[j].list.size()) +
+                              " grid=" + std::to_string(plans[j].n_cl * jobs[j].C));
+        }
         ws_off += plans[j].slab * plans[j].n_cl;
         pos += jobs[j].list.size();
+      }
+      if (prof_jobs) {
+        std::string line = "[k2 jobs] end of each job after the run's start (ms):";
+        for (size_t q = 0; q < prof_ev.size(); ++q) {
+          CU(cudaEventSynchronize(prof_ev[q]));
+          float ms = 0;
+          CU(cudaEventElapsedTime(&ms, c->ev[3], prof_ev[q]));
+          char buf[64];
+          snprintf(buf, sizeof buf, " %.1f", ms);
+          line += "  [" + prof_desc[q] + "]" + buf;
+          cudaEventDestroy(prof_ev[q]);
+        }
+        fprintf(stderr, "%s\n", line.c_str());
       }
     }
     // ---- escalation passes for pairs that ran out of slab (-6) or of pool (-4) ----
@@ -859,6 +949,7 @@ extern "C" int sfc_batch_run(sfc_ctx* c, const sfc_penalties* pen, int want_ciga
         if ((rc = ensure(c, bigger, new_cap * 4))) return rc;
         CU(cudaMemcpy(bigger.p, c->d_pool.p, std::min<size_t>((size_t)used, pool_cap) * 4, cudaMemcpyDeviceToDevice));
         // failed reservations leave holes above the old capacity but never overlap valid runs
+        c->free_cache += c->d_pool.cap;
         release(c->d_pool);
         c->d_pool = bigger;
         pool_cap = c->d_pool.cap / 4;
@@ -1468,6 +1559,7 @@ extern "C" int sfc_measure_int_peak(sfc_ctx* c, double* gops, double* mhz_est) {
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  c->free_cache += out.cap;
   release(out);
   *gops = best;
   if (mhz_est) *mhz_est = best * 1e3 / ((double)c->sm_count * 64.0);  // assuming 64 INT32 lanes/SM/clk
@@ -1496,8 +1588,7 @@ extern "C" int sfc_bio_align_batch(sfc_ctx* c, const sfc_bio_scoring* sco, const
     max_need = std::max(max_need, k4_slab_need(hp[i].m, hp[i].n));
     tot_ops += (size_t)p.pattern_len + p.text_len + 4;
   }
-  size_t free_b = 0, total_b = 0;
-  CU(cudaMemGetInfo(&free_b, &total_b));
+  const size_t free_b = device_free_bytes(c);
   size_t avail = (size_t)((double)(free_b + c->d_ws.cap) * 0.8);
   if (c->ws_limit && avail > c->ws_limit) avail = c->ws_limit;
   if (max_need > avail) return fail(c, SFC_ERR_OOM, "device workspace too small: need %zu B for one pair", max_need);
@@ -1601,8 +1692,7 @@ extern "C" int sfc_bio_score_batch(sfc_ctx* c, const sfc_bio_scoring* sco, const
   });
   const size_t stride = ((max_n + 1 + 31) & ~(size_t)31) + 32;
   const size_t per_cta = (size_t)K5_NBUF * stride * sizeof(int2);
-  size_t free_b = 0, total_b = 0;
-  CU(cudaMemGetInfo(&free_b, &total_b));
+  const size_t free_b = device_free_bytes(c);
   size_t avail = (size_t)((double)(free_b + c->d_ws.cap) * 0.8);
   if (c->ws_limit && avail > c->ws_limit) avail = c->ws_limit;
   if (per_cta > avail) return fail(c, SFC_ERR_OOM, "device workspace too small: need %zu B for one pair", per_cta);
