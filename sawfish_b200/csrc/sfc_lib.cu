@@ -604,21 +604,28 @@ static int batch_run_impl(sfc_ctx* c, const sfc_penalties* pen, int want_cigar) 
       if (const char* e = getenv("SFC_K2_SHARE_DIV")) share_div = std::max(0.25, atof(e));  // experiment knob
       const double share = std::max(total / ((double)c->sm_count * occ_guess * share_div), 2e6);
       std::vector<uint32_t> byc[4];
-      std::vector<std::pair<double, uint32_t>> tmp[4];
+      // [0..3]: cluster size 1/2/4/8; [4..7]: the same for pairs whose text is beyond K2 v2's 16-bit offsets — they get jobs
+      // of their own (round-1 kernel), so that one such pair does not take the rest of its class off K2 v2 with it
+      std::vector<std::pair<double, uint32_t>> tmp[8];
+      const bool split_v2 = a.metric == 1 && !getenv("SFC_K2_V1");
       for (size_t q = 0; q < nl; ++q) {
         int ci = 0;
         double r = est[q] / share;
         while (ci < 3 && r > 1.0) { r *= 0.5; ++ci; }
         if (force_c == 1) ci = 0; else if (force_c == 2) ci = 1; else if (force_c == 4) ci = 2; else if (force_c == 8) ci = 3;
-        tmp[ci].push_back({est[q], c->h_order[k2l_begin + q]});
+        const uint32_t pi = c->h_order[k2l_begin + q];
+        const bool over = split_v2 && c->h_pairs[pi].tlen > V2_MAX_TLEN;
+        // (such pairs are long: clusters of 4 or 8 only, which also keeps the job count within the eight work counters)
+        tmp[over ? 4 + std::max(ci, force_c ? ci : 2) : ci].push_back({est[q], pi});
       }
-      for (int ci = 3; ci >= 0; --ci) {
-        if (tmp[ci].empty()) continue;
-        std::stable_sort(tmp[ci].begin(), tmp[ci].end(), [](const std::pair<double, uint32_t>& x, const std::pair<double, uint32_t>& y) { return x.first > y.first; });
+      for (int cj = 7; cj >= 0; --cj) {
+        const int ci = cj & 3;
+        if (tmp[cj].empty()) continue;
+        std::stable_sort(tmp[cj].begin(), tmp[cj].end(), [](const std::pair<double, uint32_t>& x, const std::pair<double, uint32_t>& y) { return x.first > y.first; });
         Job j; j.threads = big_threads; j.C = 1 << ci;
         if (const char* e = getenv("SFC_K2_THREADS")) { if (a.metric != 1 || getenv("SFC_K2_V1")) j.threads = std::max(64, std::min(K2_LB_T, atoi(e))); }  // experiment knob (v1 kernel)
-        for (auto& t : tmp[ci]) j.list.push_back(t.second);
-        j.max_est = tmp[ci].front().first;  // sorted heaviest first
+        for (auto& t : tmp[cj]) j.list.push_back(t.second);
+        j.max_est = tmp[cj].front().first;  // sorted heaviest first
         jobs.push_back(std::move(j));
       }
     }
