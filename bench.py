@@ -150,6 +150,35 @@ def compact_shard(arena, pairs, idx, out=None):
     return local, sub
 
 
+def merge_rank_results(parts, n_tot, want_cigar):
+    """Host-side gather on rank 0: `parts` = one (pair indices, scores, run-length ops, ops offsets) per rank -> scores, ops and
+    ops offsets in the global pair order.  Every pair must come from exactly one rank.  No per-pair Python loop: this runs
+    inside the timed end-to-end step."""
+    g_scores = np.zeros(n_tot, np.int32)
+    seen = np.zeros(n_tot, bool)
+    g_len = np.zeros(n_tot, np.int64)
+    for idx, sc, op, off in parts:
+        assert not seen[idx].any(), "a pair was assigned to two ranks"
+        g_scores[idx] = sc
+        seen[idx] = True
+        if want_cigar:
+            g_len[idx] = np.diff(np.asarray(off, np.int64))
+    assert seen.all(), "a pair was assigned to no rank"
+    if not want_cigar:
+        return g_scores, None, None
+    g_off = np.zeros(n_tot + 1, np.int64)
+    np.cumsum(g_len, out=g_off[1:])
+    g_ops = np.zeros(int(g_off[-1]), np.uint32)
+    for idx, sc, op, off in parts:
+        off = np.asarray(off, np.int64)
+        lens = np.diff(off)
+        tot = int(off[-1] - off[0])
+        if tot:
+            dest = np.repeat(g_off[:-1][idx] - off[:-1], lens) + np.arange(int(off[0]), int(off[0]) + tot)
+            g_ops[dest] = np.asarray(op)[int(off[0]):int(off[0]) + tot]
+    return g_scores, g_ops, g_off
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -444,32 +473,7 @@ def run_leg(args, D, ctx, workload, reads, steps, warmup, cpu_budget, local_rank
         D.dist.gather_object(payload, got, dst=0, group=D.gloo)
         if rank != 0:
             return None, None, None
-        n_tot = len(glob[b][1])
-        g_scores = np.zeros(n_tot, np.int32)
-        seen = np.zeros(n_tot, bool)
-        g_len = np.zeros(n_tot, np.int64)
-        for idx, sc, op, off in got:
-            assert not seen[idx].any(), "a pair was assigned to two ranks"
-            g_scores[idx] = sc
-            seen[idx] = True
-            if want_cigar:
-                g_len[idx] = np.diff(np.asarray(off, np.int64))
-        assert seen.all(), "a pair was assigned to no rank"
-        if not want_cigar:
-            return g_scores, None, None
-        # run-length ops of every rank scattered into ONE array in global pair order (no per-pair Python loop: this is
-        # inside the timed end-to-end step)
-        g_off = np.zeros(n_tot + 1, np.int64)
-        np.cumsum(g_len, out=g_off[1:])
-        g_ops = np.zeros(int(g_off[-1]), np.uint32)
-        for idx, sc, op, off in got:
-            off = np.asarray(off, np.int64)
-            lens = np.diff(off)
-            tot = int(off[-1] - off[0])
-            if tot:
-                dest = np.repeat(g_off[:-1][idx] - off[:-1], lens) + np.arange(int(off[0]), int(off[0]) + tot)
-                g_ops[dest] = np.asarray(op)[int(off[0]):int(off[0]) + tot]
-        return g_scores, g_ops, g_off
+        return merge_rank_results(got, len(glob[b][1]), want_cigar)
 
     # ---- warm-up (also allocates device workspace) ----
     # At least W (>= 3) steps AND at least ~2.5 s: the first GPU process on a fresh box runs its first few hundred

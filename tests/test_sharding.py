@@ -102,3 +102,30 @@ def test_bench_shard_cut_covers_every_pair_once_and_compacts_exactly():
         assert (seen == 1).all()
     arena4, pairs4, groups4 = bench.make_batch("config4", 3, 5)
     assert len(groups4) == len(pairs4) and groups4.max() == 2
+
+
+def test_bench_merge_rank_results_puts_ragged_ops_back_in_global_order():
+    """bench.py's rank-0 gather (scores + ragged run-length ops of every rank -> global pair order), against a per-pair
+    reference; a pair on two ranks or on none must be refused."""
+    import bench
+    rng = np.random.default_rng(11)
+    n = 300
+    lens = rng.integers(0, 7, n)
+    truth = [rng.integers(0, 1 << 20, l).astype(np.uint32) for l in lens]
+    scores = rng.integers(-500, 0, n).astype(np.int32)
+    owner = rng.integers(0, 3, n)
+    parts = []
+    for r in range(3):
+        idx = np.flatnonzero(owner == r)
+        off = np.concatenate([[0], np.cumsum(lens[idx])]).astype(np.uint64)
+        op = np.concatenate([truth[i] for i in idx]) if len(idx) else np.zeros(0, np.uint32)
+        parts.append((idx, scores[idx], op, off))
+    g_scores, g_ops, g_off = bench.merge_rank_results(parts, n, True)
+    assert (g_scores == scores).all()
+    assert all((g_ops[int(g_off[i]):int(g_off[i + 1])] == truth[i]).all() for i in range(n))
+    s2, o2, f2 = bench.merge_rank_results(parts, n, False)
+    assert (s2 == scores).all() and o2 is None and f2 is None
+    with pytest.raises(AssertionError):
+        bench.merge_rank_results(parts + [parts[0]], n, True)   # assigned twice
+    with pytest.raises(AssertionError):
+        bench.merge_rank_results(parts[:2], n, True)            # somebody's pairs are missing
