@@ -574,7 +574,8 @@ def run_leg(args, D, ctx, workload, reads, steps, warmup, cpu_budget, local_rank
     out = {
         "metric": "alignments_per_s", "value": value, "unit": "alignments/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "warmup_done": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        # the arithmetic the dominant kernel computes in: K2 v2 works on 16-bit offsets packed two to a word, K1 on 32-bit cells
+        "vs_baseline": None, "dtype": "int16" if cfg["kernel"] == "sfc_k_align2.cuh" else "int32", "data": "synthetic",
         "config": config_dict(args, workload, reads, len(glob[0][1]) // world, world, nb),
         "gcups": all_cells_dp / (kern_ms_max * 1e-3) / 1e9,
         "wavefront_cells_per_step": int(all_cells / steps),
